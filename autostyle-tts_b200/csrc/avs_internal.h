@@ -1,0 +1,154 @@
+// Internal declarations shared by the translation units of libavs.so.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/avs.h"
+
+typedef unsigned long long u64;
+
+#define AVS_GROUP_ROWS 256      // sampling / tiling granularity of the scan (rows)
+#define AVS_MAX_KPRIME 256      // largest oversampled candidate list
+#define AVS_REPAIR_CAP 4096     // exact-repair collection buffer per flagged query
+#define AVS_MAX_REPAIR_Q 256    // flagged queries repaired per search
+#define AVS_MAX_LEVELS 6
+
+// ---- error plumbing -------------------------------------------------------------------------
+void avs_set_error(const char* fmt, ...);
+#define AVS_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            avs_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                          __LINE__);                                                           \
+            return AVS_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+#define AVS_CHECK(expr)                                                                        \
+    do {                                                                                       \
+        int _r = (expr);                                                                       \
+        if (_r != AVS_OK) return _r;                                                           \
+    } while (0)
+
+// ---- order-preserving keys ------------------------------------------------------------------
+// key = (monotone(float score) << 32) | (0xFFFFFFFF - row): a larger key is a better
+// candidate (higher score, then smaller row).  Key 0 is below every real key.
+__host__ __device__ __forceinline__ uint32_t avs_f2ord(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+#endif
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ float avs_ord2f(uint32_t o) {
+    uint32_t b = o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ u64 avs_make_key(float s, uint32_t row) {
+    return ((u64)avs_f2ord(s) << 32) | (u64)(0xFFFFFFFFu - row);
+}
+__host__ __device__ __forceinline__ uint32_t avs_key_row(u64 k) {
+    return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
+}
+__host__ __device__ __forceinline__ float avs_key_score(u64 k) { return avs_ord2f((uint32_t)(k >> 32)); }
+
+// ---- one sampling level of the scan ---------------------------------------------------------
+// A level visits row groups g = j*stride (j = 0..n_iter-1), skipping those with
+// g % skip == 0 when skip != 0 (they were visited by an earlier, sparser level).
+struct AvsLevel {
+    int64_t n_iter;
+    int64_t stride;
+    int64_t skip;
+};
+
+struct AvsScratch {
+    // query preparation
+    float* qf = nullptr;          // [nq_pad, dpad] fp32, normalised for COSINE, zero padded
+    __nv_bfloat16* qb = nullptr;  // [nq_pad, dpad] bf16 of qf
+    double* qnorm = nullptr;      // [nq] ||q|| in float64
+    float* eps_gemv = nullptr;    // [nq] certificate slack for the fp32-query scan
+    float* eps_gemm = nullptr;    // [nq] certificate slack for the bf16-query scan
+    // candidate collection
+    u64* cand = nullptr;          // [nq, cap]
+    int* cnt = nullptr;           // [nq]
+    u64* tau = nullptr;           // [nq_pad] running threshold key
+    u64* topkeys = nullptr;       // [nq, kprime] final bf16-scan candidates, sorted desc
+    int* topn = nullptr;          // [nq]
+    int* status = nullptr;        // [nq] bit0 overflow, bit1 underflow, bit2 cert failed, bit3 uncertified
+    double* s64 = nullptr;        // [nq, kprime] exact scores of the candidates
+    int64_t* cid = nullptr;       // [nq, kprime] primary keys of the candidates
+    double* out_s64 = nullptr;    // [nq, k] exact scores of the final hits (for the shard merge)
+    // repair
+    int* flagged = nullptr;       // [1 + AVS_MAX_REPAIR_Q] count, then query indices
+    double* rep_s = nullptr;      // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
+    uint32_t* rep_row = nullptr;  // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
+    int* rep_cnt = nullptr;       // [AVS_MAX_REPAIR_Q]
+    double* rep_thr = nullptr;    // [AVS_MAX_REPAIR_Q]
+    // sharded search
+    void* gather_send = nullptr;  // [nq, k] (f64 score, i64 id)
+    void* gather_recv = nullptr;  // [world, nq, k]
+    // host staging for avs_search_host
+    float* h2d_q = nullptr;
+    int64_t* d_ids = nullptr;
+    float* d_scores = nullptr;
+    int64_t* d_rows = nullptr;
+    // sizes the buffers were allocated for
+    size_t gather_items = 0;
+    int nq_cap = 0, kprime_cap = 0, cap_cap = 0, k_cap = 0, world_cap = 0, host_nq_cap = 0, host_k_cap = 0;
+};
+
+struct avs_store {
+    int device = 0;
+    int dim = 0;
+    int dpad = 0;             // dim rounded up to 64 (one 128-byte swizzle atom of bf16)
+    int metric = 0;
+    int64_t capacity = 0;     // rows allocated (multiple of AVS_GROUP_ROWS)
+    int64_t count = 0;
+    float* master = nullptr;          // [capacity, dim] fp32 rows exactly as inserted
+    __nv_bfloat16* xb = nullptr;      // [capacity, dpad] bf16 scan copy (unit rows for COSINE)
+    float* inv_norm = nullptr;        // [capacity] 1/||x|| (0 for zero rows)
+    int64_t* ids = nullptr;           // [capacity]
+    float* gstat = nullptr;           // [4] device scalars: r_max, xnorm_max (non-negative, atomicMax on bits)
+    unsigned long long* dstat = nullptr;  // [8] device counters: repaired, uncertified
+    AvsScratch sc;
+    int num_sms = 148;
+    // options
+    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 1 << 30, opt_ratio = 32, opt_force_repair = 0;
+    // stats
+    int64_t st_launches = 0, st_searches = 0, st_queries = 0;
+    int st_last_kprime = 0, st_last_levels = 0, st_last_path = 0;
+    // scan timing hook
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   // event pairs around the dominant scan launches
+    size_t tev_used = 0;
+    // gemm path (tensor maps etc.)
+    void* gemm_state = nullptr;
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+// ---- host entry points implemented across translation units ----------------------------------
+int avs_launch_prep(avs_store* s, const float* q, int nq, cudaStream_t st);
+int avs_launch_scan_gemv(avs_store* s, int q0, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
+int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
+void avs_gemm_state_free(avs_store* s);
+int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
+                     int64_t* out_rows, cudaStream_t st);
+int avs_scratch_reserve(avs_store* s, int nq, int kprime, int cap, int k);
+void avs_scratch_free(avs_store* s);
+void avs_comm_free(avs_store* s);

@@ -1,0 +1,654 @@
+// Search pipeline around the scan kernels:
+//   prep_queries  -> [scan level l -> select level l]* -> rescore_f64 -> finalize (+certificate)
+//   -> repair_scan / repair_finalize (device-gated: exit at once unless a query was flagged)
+// Replaces the arithmetic behind `MilvusClient.search`
+// (/root/reference/milvus/search_embeddings.py:15-22, /root/reference/milvus/RAG.py:383-390).
+#include <math.h>
+
+#include <vector>
+
+#include "avs_internal.h"
+
+#define ST_OVERFLOW 1
+#define ST_CERT_FAIL 4
+#define ST_UNCERTIFIED 8
+
+static int pow2ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Query preparation.  One CTA per (padded) query slot.  COSINE: qf = q / ||q|| (norm in float64).
+// Writes the fp32 copy for the gemv scan, its bf16 rounding for the tensor-core scan, ||q|| in
+// float64 for the exact rescoring and the two rigorous certificate slacks:
+//   |scan score - exact score| <= ||q_scan|| * r_max + ||q_scan - qf|| * xmax + accumulation bound
+// with r_max = max_j ||bf16(x^_j) - x^_j|| (maintained by K1) and xmax = max ||x^_j||.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_f64(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int dpad,
+                                                           int metric, const float* __restrict__ gstat,
+                                                           float* __restrict__ qf, __nv_bfloat16* __restrict__ qb,
+                                                           double* __restrict__ qnorm, float* __restrict__ eps_gemv,
+                                                           float* __restrict__ eps_gemm, u64* __restrict__ tau,
+                                                           int* __restrict__ cnt, int* __restrict__ status) {
+    __shared__ double sh[4];
+    const int qi = blockIdx.x;
+    float* of = qf + (size_t)qi * dpad;
+    __nv_bfloat16* ob = qb + (size_t)qi * dpad;
+    if (qi >= nq) {  // padding slot: zero vector, never accepts
+        for (int c = threadIdx.x; c < dpad; c += blockDim.x) {
+            of[c] = 0.f;
+            ob[c] = __float2bfloat16_rn(0.f);
+        }
+        if (threadIdx.x == 0) { tau[qi] = ~0ull; cnt[qi] = 0; }
+        return;
+    }
+    const float* x = q + (size_t)qi * dim;
+    double ss = 0.0;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        double v = (double)x[c];
+        ss += v * v;
+    }
+    ss = block_sum_f64(ss, sh);
+    const double qn = sqrt(ss);
+    const float scale = (metric == AVS_METRIC_COSINE) ? (qn > 0.0 ? (float)(1.0 / qn) : 0.f) : 1.0f;
+    double nf = 0.0, nb = 0.0, ne = 0.0;
+    for (int c = threadIdx.x; c < dpad; c += blockDim.x) {
+        float v = c < dim ? x[c] * scale : 0.f;
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        float bv = __bfloat162float(b);
+        of[c] = v;
+        ob[c] = b;
+        nf += (double)v * v;
+        nb += (double)bv * bv;
+        ne += (double)(bv - v) * (double)(bv - v);
+    }
+    nf = block_sum_f64(nf, sh);
+    nb = block_sum_f64(nb, sh);
+    ne = block_sum_f64(ne, sh);
+    if (threadIdx.x == 0) {
+        const double r_max = (double)gstat[0] * 1.0001 + 1e-7;
+        const double xmax = (metric == AVS_METRIC_COSINE) ? 1.00001 : (double)gstat[1] * 1.00001;
+        const double n_f = sqrt(nf), n_b = sqrt(nb), e_q = sqrt(ne);
+        // fp32 FMA chains (gemv) and tensor-core fp32 accumulation (gemm): n*u*|q||x| style bounds,
+        // doubled; plus the fp32 rounding of the normalised operands themselves.
+        const double acc_v = (((double)dpad / 32.0 + 8.0) * 1.2e-7 + 1e-6) * n_f * xmax;
+        const double acc_m = ((double)dpad * 1.2e-7 + 1e-6) * n_b * xmax;
+        qnorm[qi] = qn;
+        eps_gemv[qi] = (float)(n_f * r_max + acc_v);
+        eps_gemm[qi] = (float)(n_b * r_max + e_q * xmax + acc_m);
+        tau[qi] = 0ull;
+        cnt[qi] = 0;
+        status[qi] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level select (K4).  One CTA per query: bitonic sort (descending) of the collected keys in
+// shared memory.  Intermediate level: the rank-j key becomes the next level's threshold and the
+// survivors stay in the buffer.  Final level: the best K' keys are the candidate list and
+// `bound` is an upper bound on the scan score of every row NOT in the list.
+// ---------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(u64* sm, int P) {
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool desc = (i & k2) == 0;
+                    const u64 a = sm[i], b = sm[ixj];
+                    if (desc ? (a < b) : (a > b)) { sm[i] = b; sm[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) select_level_kernel(u64* __restrict__ cand, int* __restrict__ cnt, int cap,
+                                                            u64* __restrict__ tau, int j_rank, int is_final,
+                                                            int kprime, int64_t n_rows, u64* __restrict__ topkeys,
+                                                            int* __restrict__ topn, float* __restrict__ bound,
+                                                            int* __restrict__ status) {
+    extern __shared__ u64 sm[];
+    const int q = blockIdx.x;
+    const int total = cnt[q];
+    const int n = total < cap ? total : cap;
+    int P = 32;
+    while (P < n) P <<= 1;
+    u64* c = cand + (size_t)q * cap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sm[i] = i < n ? c[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(sm, P);
+    if (!is_final) {
+        int jj = j_rank;
+        if (total > cap) {  // overflowed: the kept entries are a 1/phi subsample of the survivors
+            jj = (int)(((long long)j_rank * cap) / total);
+            if (jj < 1) jj = 1;
+        }
+        const int keep = n >= jj ? jj : n;
+        for (int i = threadIdx.x; i < keep; i += blockDim.x) c[i] = sm[i];
+        if (threadIdx.x == 0) {
+            if (n >= jj) tau[q] = sm[jj - 1];
+            cnt[q] = keep;
+            if (total > cap) status[q] |= ST_OVERFLOW;  // rows were lost for good: force the exact repair
+        }
+    } else {
+        const int m = n < kprime ? n : kprime;
+        for (int i = threadIdx.x; i < kprime; i += blockDim.x) topkeys[(size_t)q * kprime + i] = i < m ? sm[i] : 0ull;
+        if (threadIdx.x == 0) {
+            topn[q] = m;
+            float b;
+            int st = 0;
+            if (total > cap || (status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }  // lost entries
+            else if ((int64_t)n >= n_rows) b = -INFINITY;                // every row is a candidate
+            else if (n > kprime) b = avs_key_score(sm[kprime - 1]);      // rows outside <= K'-th key
+            else b = tau[q] == 0ull ? -INFINITY : avs_key_score(tau[q]); // rows outside < threshold
+            bound[q] = b;
+            status[q] |= st;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact float64 score of one master row, one warp per (query, candidate).  Lane l accumulates
+// elements l, l+32, ... in order, then an xor-butterfly (commutative, so every lane ends with the
+// same bits).  The result depends only on the row's and the query's content: identical rows tie
+// exactly and fall through to the id comparison.  Used by both rescoring and repair.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_score(const float* __restrict__ x, const float* __restrict__ q, int dim,
+                                              double qn, int metric, int lane) {
+    double dot = 0.0, xx = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+        const double a = (double)__ldg(x + c), b = (double)__ldg(q + c);
+        dot = fma(a, b, dot);
+        xx = fma(a, a, xx);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    }
+    if (metric == AVS_METRIC_COSINE) {
+        const double den = sqrt(xx) * qn;
+        return den > 0.0 ? dot / den : 0.0;
+    }
+    return dot;
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ master, const int64_t* __restrict__ ids,
+                                                      const float* __restrict__ q, const double* __restrict__ qnorm,
+                                                      const u64* __restrict__ topkeys, const int* __restrict__ topn,
+                                                      int nq, int kprime, int dim, int metric,
+                                                      double* __restrict__ s64, int64_t* __restrict__ cid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)nq * kprime) return;
+    const int qi = (int)(w / kprime), c = (int)(w - (int64_t)qi * kprime);
+    if (c >= topn[qi]) {
+        if (lane == 0) { s64[w] = -INFINITY; cid[w] = -1; }
+        return;
+    }
+    const uint32_t row = avs_key_row(topkeys[w]);
+    const double s = exact_score(master + (size_t)row * dim, q + (size_t)qi * dim, dim, qnorm[qi], metric, lane);
+    if (lane == 0) { s64[w] = s; cid[w] = ids[row]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalize: one CTA per query sorts the <= 256 rescored candidates by (score desc, id asc, row asc)
+// and checks the exactness certificate: every row outside the candidate list has scan score
+// <= bound, hence exact score <= bound + eps; if the k-th exact score is strictly larger, the
+// top-k is proven exact.  Otherwise the query is queued for the exact repair scan.
+// ---------------------------------------------------------------------------------------------
+struct Hit { double s; int64_t id; uint32_t row; };
+__device__ __forceinline__ bool hit_better(const Hit& a, const Hit& b) {
+    if (a.s != b.s) return a.s > b.s;
+    if (a.id != b.id) return a.id < b.id;
+    return a.row < b.row;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ s64, const int64_t* __restrict__ cid,
+                                                       const u64* __restrict__ topkeys, const int* __restrict__ topn,
+                                                       const float* __restrict__ bound, const float* __restrict__ eps,
+                                                       int kprime, int k, int64_t n_rows, int force_repair,
+                                                       int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                                                       int64_t* __restrict__ out_rows, double* __restrict__ out_s64,
+                                                       int* __restrict__ status, int* __restrict__ flagged,
+                                                       double* __restrict__ rep_thr, int* __restrict__ rep_cnt,
+                                                       u64* __restrict__ dstat) {
+    __shared__ Hit sm[AVS_MAX_KPRIME];
+    const int q = blockIdx.x, t = threadIdx.x;
+    const int n = topn[q];
+    if (t < kprime) {
+        Hit h;
+        if (t < n) { h.s = s64[(size_t)q * kprime + t]; h.id = cid[(size_t)q * kprime + t]; h.row = avs_key_row(topkeys[(size_t)q * kprime + t]); }
+        else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
+        sm[t] = h;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= kprime; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (t < kprime) {
+                const int ixj = t ^ j;
+                if (ixj > t) {
+                    const bool desc = (t & k2) == 0;
+                    const Hit a = sm[t], b = sm[ixj];
+                    if (desc ? hit_better(b, a) : hit_better(a, b)) { sm[t] = b; sm[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (t < k) {
+        const bool valid = t < n;
+        out_ids[(size_t)q * k + t] = valid ? sm[t].id : -1;
+        out_scores[(size_t)q * k + t] = valid ? (float)sm[t].s : -INFINITY;
+        if (out_rows) out_rows[(size_t)q * k + t] = valid ? (int64_t)sm[t].row : -1;
+        out_s64[(size_t)q * k + t] = valid ? sm[t].s : -INFINITY;
+    }
+    if (t == 0) {
+        const int need = (int64_t)k < n_rows ? k : (int)n_rows;
+        const float b = bound[q];
+        bool ok = n >= need;
+        if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
+        if (force_repair) ok = false;
+        if (!ok) {
+            const int pos = atomicAdd(flagged, 1);
+            if (pos < AVS_MAX_REPAIR_Q) {
+                flagged[1 + pos] = q;
+                rep_thr[pos] = (n >= need && need > 0) ? sm[need - 1].s : -INFINITY;
+                rep_cnt[pos] = 0;
+                status[q] |= ST_CERT_FAIL;
+            } else {
+                status[q] |= ST_CERT_FAIL | ST_UNCERTIFIED;
+                atomicAdd(dstat + 1, 1ull);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact repair.  For every flagged query: float64 brute force over the fp32 master, collecting all
+// rows whose exact score reaches the k-th best exact score already known (a valid lower bound of
+// the true k-th best).  The collected set contains the true top-k; it is sorted exactly.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) repair_scan_kernel(const float* __restrict__ master, const float* __restrict__ q,
+                                                          const double* __restrict__ qnorm, int64_t n_rows, int dim,
+                                                          int metric, const int* __restrict__ flagged,
+                                                          const double* __restrict__ rep_thr, double* __restrict__ rep_s,
+                                                          uint32_t* __restrict__ rep_row, int* __restrict__ rep_cnt) {
+    int nf = flagged[0];
+    if (nf == 0) return;
+    if (nf > AVS_MAX_REPAIR_Q) nf = AVS_MAX_REPAIR_Q;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int f = 0; f < nf; ++f) {
+        const int qi = flagged[1 + f];
+        const double thr = rep_thr[f], qn = qnorm[qi];
+        const float* qp = q + (size_t)qi * dim;
+        for (int64_t r = warp; r < n_rows; r += nwarps) {
+            const double s = exact_score(master + (size_t)r * dim, qp, dim, qn, metric, lane);
+            if (lane == 0 && s >= thr) {
+                const int pos = atomicAdd(rep_cnt + f, 1);
+                if (pos < AVS_REPAIR_CAP) {
+                    rep_s[(size_t)f * AVS_REPAIR_CAP + pos] = s;
+                    rep_row[(size_t)f * AVS_REPAIR_CAP + pos] = (uint32_t)r;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) repair_finalize_kernel(const int* __restrict__ flagged, const double* __restrict__ rep_s,
+                                                               const uint32_t* __restrict__ rep_row, const int* __restrict__ rep_cnt,
+                                                               const int64_t* __restrict__ ids, int k, int64_t n_rows,
+                                                               int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                                                               int64_t* __restrict__ out_rows, double* __restrict__ out_s64,
+                                                               int* __restrict__ status, u64* __restrict__ dstat) {
+    extern __shared__ unsigned char raw[];
+    Hit* sm = reinterpret_cast<Hit*>(raw);
+    int nf = flagged[0];
+    if (nf > AVS_MAX_REPAIR_Q) nf = AVS_MAX_REPAIR_Q;
+    const int f = blockIdx.x;
+    if (f >= nf) return;
+    const int q = flagged[1 + f];
+    const int total = rep_cnt[f];
+    const int need = (int64_t)k < n_rows ? k : (int)n_rows;
+    if (total > AVS_REPAIR_CAP || total < need) {  // too many ties at the threshold: keep phase-1 output
+        if (threadIdx.x == 0) { status[q] |= ST_UNCERTIFIED; atomicAdd(dstat + 1, 1ull); }
+        return;
+    }
+    int P = 32;
+    while (P < total) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        Hit h;
+        if (i < total) { h.s = rep_s[(size_t)f * AVS_REPAIR_CAP + i]; h.row = rep_row[(size_t)f * AVS_REPAIR_CAP + i]; h.id = ids[h.row]; }
+        else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
+        sm[i] = h;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool desc = (i & k2) == 0;
+                    const Hit a = sm[i], b = sm[ixj];
+                    if (desc ? hit_better(b, a) : hit_better(a, b)) { sm[i] = b; sm[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const bool valid = t < total;
+        out_ids[(size_t)q * k + t] = valid ? sm[t].id : -1;
+        out_scores[(size_t)q * k + t] = valid ? (float)sm[t].s : -INFINITY;
+        if (out_rows) out_rows[(size_t)q * k + t] = valid ? (int64_t)sm[t].row : -1;
+        out_s64[(size_t)q * k + t] = valid ? sm[t].s : -INFINITY;
+    }
+    if (threadIdx.x == 0) atomicAdd(dstat + 0, 1ull);
+}
+
+__global__ void fill_empty_kernel(int64_t* ids, float* scores, int64_t* rows, double* s64, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        ids[i] = -1;
+        scores[i] = -INFINITY;
+        if (rows) rows[i] = -1;
+        if (s64) s64[i] = -INFINITY;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scratch management
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        avs_set_error("out of device memory allocating %zu bytes of search scratch", n * sizeof(T));
+        return AVS_E_NOMEM;
+    }
+    return AVS_OK;
+}
+
+void avs_scratch_free(avs_store* s) {
+    AvsScratch& c = s->sc;
+    cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
+    cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
+    cudaFree(c.s64); cudaFree(c.cid); cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.rep_s); cudaFree(c.rep_row);
+    cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
+    cudaFree(c.d_ids); cudaFree(c.d_scores); cudaFree(c.d_rows);
+    if (c.h2d_q) cudaFree(c.h2d_q);
+    c = AvsScratch();
+}
+
+// bound[] lives behind eps_gemm in one allocation to keep the struct small
+static float* g_bound_of(AvsScratch& c) { return c.eps_gemm + c.nq_cap; }
+
+int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
+    AvsScratch& c = s->sc;
+    const bool grow_q = nq_pad > c.nq_cap, grow_kp = kprime > c.kprime_cap, grow_cap = cap > c.cap_cap, grow_k = k > c.k_cap;
+    if (!(grow_q || grow_kp || grow_cap || grow_k)) return AVS_OK;
+    AVS_CUDA(cudaDeviceSynchronize());
+    const int nq2 = grow_q ? nq_pad : c.nq_cap, kp2 = grow_kp ? kprime : c.kprime_cap;
+    const int cap2 = grow_cap ? cap : c.cap_cap, k2 = grow_k ? k : c.k_cap;
+    if (grow_q) {
+        AVS_CHECK(dev_alloc(&c.qf, (size_t)nq2 * s->dpad));
+        AVS_CHECK(dev_alloc(&c.qb, (size_t)nq2 * s->dpad));
+        AVS_CHECK(dev_alloc(&c.qnorm, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.eps_gemv, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.eps_gemm, (size_t)nq2 * 2));  // eps_gemm | bound
+        AVS_CHECK(dev_alloc(&c.cnt, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.tau, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.topn, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.status, (size_t)nq2));
+    }
+    if (grow_q || grow_cap) AVS_CHECK(dev_alloc(&c.cand, (size_t)nq2 * cap2));
+    if (grow_q || grow_kp) {
+        AVS_CHECK(dev_alloc(&c.topkeys, (size_t)nq2 * kp2));
+        AVS_CHECK(dev_alloc(&c.s64, (size_t)nq2 * kp2));
+        AVS_CHECK(dev_alloc(&c.cid, (size_t)nq2 * kp2));
+    }
+    if (grow_q || grow_k) AVS_CHECK(dev_alloc(&c.out_s64, (size_t)nq2 * k2));
+    if (!c.flagged) {
+        AVS_CHECK(dev_alloc(&c.flagged, (size_t)1 + AVS_MAX_REPAIR_Q));
+        AVS_CHECK(dev_alloc(&c.rep_s, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
+        AVS_CHECK(dev_alloc(&c.rep_row, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
+        AVS_CHECK(dev_alloc(&c.rep_cnt, (size_t)AVS_MAX_REPAIR_Q));
+        AVS_CHECK(dev_alloc(&c.rep_thr, (size_t)AVS_MAX_REPAIR_Q));
+    }
+    c.nq_cap = nq2; c.kprime_cap = kp2; c.cap_cap = cap2; c.k_cap = k2;
+    return AVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan timing hook (bench.py roofline): event pairs around the dominant (final-level) scan launch
+// ---------------------------------------------------------------------------------------------
+extern "C" int avs_scan_timing(avs_store* s, int enable_reset, double* mean_ms, int64_t* launches) {
+    if (!s) { avs_set_error("avs_scan_timing: NULL store"); return AVS_E_INVALID; }
+    AVS_CUDA(cudaSetDevice(s->device));
+    if (mean_ms || launches) {
+        double tot = 0.0;
+        for (size_t i = 0; i < s->tev_used; ++i) {
+            AVS_CUDA(cudaEventSynchronize(s->tev[2 * i + 1]));
+            float ms = 0.f;
+            AVS_CUDA(cudaEventElapsedTime(&ms, s->tev[2 * i], s->tev[2 * i + 1]));
+            tot += ms;
+        }
+        if (mean_ms) *mean_ms = s->tev_used ? tot / (double)s->tev_used : 0.0;
+        if (launches) *launches = (int64_t)s->tev_used;
+    }
+    if (enable_reset >= 0) {
+        s->timing = enable_reset != 0;
+        s->tev_used = 0;
+    }
+    return AVS_OK;
+}
+
+static bool timing_begin(avs_store* s, cudaStream_t st, size_t* slot) {
+    if (!s->timing || s->tev_used >= 8192) return false;
+    if (2 * s->tev_used >= s->tev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+        s->tev.push_back(a);
+        s->tev.push_back(b);
+    }
+    *slot = s->tev_used++;
+    cudaEventRecord(s->tev[2 * *slot], st);
+    return true;
+}
+static void timing_end(avs_store* s, cudaStream_t st, size_t slot) { cudaEventRecord(s->tev[2 * slot + 1], st); }
+
+// ---------------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------------
+int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
+                     int64_t* out_rows, cudaStream_t st) {
+    if (!s) { avs_set_error("avs_search: NULL store"); return AVS_E_INVALID; }
+    if (nq < 0 || (nq > 0 && (!q || !out_ids || !out_scores))) { avs_set_error("avs_search: NULL query/output buffer"); return AVS_E_INVALID; }
+    if (k < 1 || k > AVS_MAX_KPRIME) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
+    if (nq == 0) return AVS_OK;
+    if (nq > (1 << 20)) { avs_set_error("avs_search: more than 2^20 queries in one call"); return AVS_E_INVALID; }
+    AVS_CUDA(cudaSetDevice(s->device));
+    s->st_searches++;
+    s->st_queries += nq;
+
+    int kprime = s->opt_oversample > 0 ? pow2ceil(s->opt_oversample) : pow2ceil(2 * k + 8);
+    if (kprime < 16) kprime = 16;
+    if (kprime > AVS_MAX_KPRIME) kprime = AVS_MAX_KPRIME;
+    if (kprime < k) kprime = pow2ceil(k);
+    int cap = pow2ceil(48 * kprime);
+    if (cap < 1024) cap = 1024;
+    if (cap > 16384) cap = 16384;
+    const int nq_pad = (nq + 255) / 256 * 256;
+    AVS_CHECK(avs_scratch_reserve(s, nq_pad, kprime, cap, k));
+    AvsScratch& c = s->sc;
+    float* bound = g_bound_of(c);
+
+    if (s->count == 0) {
+        const int64_t n = (int64_t)nq * k;
+        fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_ids, out_scores, out_rows, c.out_s64, n);
+        s->st_launches++;
+        AVS_CUDA(cudaGetLastError());
+        return AVS_OK;
+    }
+
+    // sampling levels: the sparsest level must fit the collection buffer with threshold 0
+    const int64_t G = (s->count + AVS_GROUP_ROWS - 1) / AVS_GROUP_ROWS;
+    const int64_t rho = s->opt_ratio < 2 ? 2 : s->opt_ratio;
+    int L = 1;
+    int64_t stride0 = 1;
+    while (((G + stride0 - 1) / stride0) * AVS_GROUP_ROWS > cap && L < AVS_MAX_LEVELS) { stride0 *= rho; ++L; }
+    AvsLevel lv[AVS_MAX_LEVELS];
+    {
+        int64_t stride = stride0, prev = 0;
+        for (int i = 0; i < L; ++i) {
+            lv[i].stride = stride;
+            lv[i].n_iter = (G + stride - 1) / stride;
+            lv[i].skip = prev;
+            prev = stride;
+            stride /= rho;
+        }
+    }
+    int j_rank = (int)((16ll * kprime) / rho);
+    if (j_rank < 8) j_rank = 8;
+
+    const bool use_gemm = (s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch);
+    s->st_last_kprime = kprime;
+    s->st_last_levels = L;
+    s->st_last_path = use_gemm ? 2 : 1;
+
+    AVS_CUDA(cudaMemsetAsync(c.flagged, 0, sizeof(int), st));
+    prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
+                                                c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status);
+    s->st_launches++;
+    AVS_CUDA(cudaGetLastError());
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        AVS_CUDA(cudaFuncSetAttribute(select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        AVS_CUDA(cudaFuncSetAttribute(repair_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(AVS_REPAIR_CAP * sizeof(Hit))));
+        attr_done = true;
+    }
+
+    for (int l = 0; l < L; ++l) {
+        const bool final_level = (l == L - 1);
+        size_t slot = 0;
+        const bool timed = final_level && timing_begin(s, st, &slot);
+        if (use_gemm) {
+            AVS_CHECK(avs_launch_scan_gemm(s, nq, lv[l], cap, st));
+        } else {
+            for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
+        }
+        if (timed) timing_end(s, st, slot);
+        select_level_kernel<<<nq, 256, (size_t)cap * 8, st>>>(c.cand, c.cnt, cap, c.tau, j_rank, final_level ? 1 : 0,
+                                                               kprime, s->count, c.topkeys, c.topn, bound, c.status);
+        s->st_launches++;
+        AVS_CUDA(cudaGetLastError());
+    }
+
+    {
+        const int64_t warps = (int64_t)nq * kprime;
+        rescore_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(s->master, s->ids, q, c.qnorm, c.topkeys, c.topn, nq,
+                                                                    kprime, s->dim, s->metric, c.s64, c.cid);
+        s->st_launches++;
+        AVS_CUDA(cudaGetLastError());
+    }
+    finalize_kernel<<<nq, 256, 0, st>>>(c.s64, c.cid, c.topkeys, c.topn, bound, use_gemm ? c.eps_gemm : c.eps_gemv, kprime, k,
+                                        s->count, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
+                                        c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
+    s->st_launches++;
+    AVS_CUDA(cudaGetLastError());
+    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, c.flagged,
+                                                       c.rep_thr, c.rep_s, c.rep_row, c.rep_cnt);
+    s->st_launches++;
+    AVS_CUDA(cudaGetLastError());
+    const int rep_blocks = nq < AVS_MAX_REPAIR_Q ? nq : AVS_MAX_REPAIR_Q;
+    repair_finalize_kernel<<<rep_blocks, 1024, AVS_REPAIR_CAP * sizeof(Hit), st>>>(
+        c.flagged, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, s->count, out_ids, out_scores, out_rows, c.out_s64, c.status,
+        s->dstat);
+    s->st_launches++;
+    AVS_CUDA(cudaGetLastError());
+    return AVS_OK;
+}
+
+extern "C" int avs_search(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
+                          int64_t* out_rows, void* stream) {
+    return avs_search_local(s, q, nq, k, out_ids, out_scores, out_rows, (cudaStream_t)stream);
+}
+
+extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k, int64_t* out_ids_host,
+                               float* out_scores_host, int64_t* out_rows_host) {
+    if (!s) { avs_set_error("avs_search_host: NULL store"); return AVS_E_INVALID; }
+    if (nq < 0 || (nq > 0 && (!q_host || !out_ids_host || !out_scores_host))) { avs_set_error("avs_search_host: NULL buffer"); return AVS_E_INVALID; }
+    if (k < 1 || k > AVS_MAX_KPRIME) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
+    if (nq == 0) return AVS_OK;
+    AVS_CUDA(cudaSetDevice(s->device));
+    AvsScratch& c = s->sc;
+    if (nq > c.host_nq_cap || k > c.host_k_cap) {
+        AVS_CUDA(cudaDeviceSynchronize());
+        const int nq2 = nq > c.host_nq_cap ? nq : c.host_nq_cap, k2 = k > c.host_k_cap ? k : c.host_k_cap;
+        AVS_CHECK(dev_alloc(&c.h2d_q, (size_t)nq2 * s->dim));
+        AVS_CHECK(dev_alloc(&c.d_ids, (size_t)nq2 * k2));
+        AVS_CHECK(dev_alloc(&c.d_scores, (size_t)nq2 * k2));
+        AVS_CHECK(dev_alloc(&c.d_rows, (size_t)nq2 * k2));
+        c.host_nq_cap = nq2; c.host_k_cap = k2;
+    }
+    cudaStream_t st = 0;
+    AVS_CUDA(cudaMemcpyAsync(c.h2d_q, q_host, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    AVS_CHECK(avs_search_local(s, c.h2d_q, nq, k, c.d_ids, c.d_scores, c.d_rows, st));
+    AVS_CUDA(cudaMemcpyAsync(out_ids_host, c.d_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AVS_CUDA(cudaMemcpyAsync(out_scores_host, c.d_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_rows_host) AVS_CUDA(cudaMemcpyAsync(out_rows_host, c.d_rows, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AVS_CUDA(cudaStreamSynchronize(st));
+    return AVS_OK;
+}
+
+extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
+    if (!s || !key) { avs_set_error("avs_set_option: NULL argument"); return AVS_E_INVALID; }
+    std::string k(key);
+    if (k == "scan_path") s->opt_scan_path = (int)value;
+    else if (k == "oversample") s->opt_oversample = (int)value;
+    else if (k == "gemm_min_batch") s->opt_gemm_min_batch = (int)value;
+    else if (k == "levels_ratio") s->opt_ratio = (int)value;
+    else if (k == "force_repair") s->opt_force_repair = (int)value;
+    else { avs_set_error("avs_set_option: unknown option '%s'", key); return AVS_E_INVALID; }
+    return AVS_OK;
+}
+
+extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
+    if (!s || !key || !out) { avs_set_error("avs_get_stat: NULL argument"); return AVS_E_INVALID; }
+    std::string k(key);
+    if (k == "kernel_launches") *out = s->st_launches;
+    else if (k == "searches") *out = s->st_searches;
+    else if (k == "queries") *out = s->st_queries;
+    else if (k == "last_kprime") *out = s->st_last_kprime;
+    else if (k == "last_levels") *out = s->st_last_levels;
+    else if (k == "last_scan_path") *out = s->st_last_path;
+    else if (k == "repaired_queries" || k == "uncertified_queries") {
+        AVS_CUDA(cudaSetDevice(s->device));
+        u64 h[2];
+        AVS_CUDA(cudaMemcpy(h, s->dstat, sizeof(h), cudaMemcpyDeviceToHost));
+        *out = (int64_t)(k == "repaired_queries" ? h[0] : h[1]);
+    } else { avs_set_error("avs_get_stat: unknown stat '%s'", key); return AVS_E_INVALID; }
+    return AVS_OK;
+}

@@ -1,0 +1,146 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/avs.h declares, the host
+side of the drop-in behaves like the reference's pymilvus surface, and the product path fails
+loudly (never silently on the CPU) when no B200 is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu, load_pkg
+
+
+def test_header_symbols_all_exported(pkg):
+    hdr = open(os.path.join(ROOT, "include", "avs.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(avs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg.ABI_SYMBOLS), declared ^ set(pkg.ABI_SYMBOLS)
+    lib = pkg.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"libavs.so does not export {name}"
+    assert b"sm_100a" in lib.avs_version()
+
+
+def test_error_convention_without_compute(pkg):
+    lib = pkg.load_library()
+    out = ctypes.c_void_p()
+    assert lib.avs_create(0, 0, 0, 10, ctypes.byref(out)) == -1          # dim 0 -> AVS_E_INVALID
+    assert b"dim" in lib.avs_last_error()
+    assert lib.avs_create(0, 8, 7, 10, ctypes.byref(out)) == -1          # unknown metric
+    assert lib.avs_search(None, None, 1, 1, None, None, None, None) == -1
+    assert b"NULL store" in lib.avs_last_error()
+    assert lib.avs_count(None) == 0
+    assert lib.avs_destroy(None) == 0
+
+
+@pytest.mark.skipif(has_gpu(), reason="CPU-only behaviour")
+def test_no_cpu_fallback(pkg):
+    """Without a GPU the engine refuses to construct; the client surfaces it as an Exception."""
+    with pytest.raises(pkg.AvsError):
+        pkg.Store(8, "COSINE")
+    c = pkg.MilvusClient(":memory:")
+    c.create_collection("t", dimension=4)
+    with pytest.raises(pkg.MilvusException):
+        c.insert("t", [{"id": 1, "vector": [1, 0, 0, 0]}])
+    assert c.search("t", data=[[1, 0, 0, 0]], limit=3) == [[]]            # empty collection: one empty list per query
+
+
+def test_schema_types_match_pymilvus_surface(pkg):
+    DataType, FieldSchema, CollectionSchema = pkg.DataType, pkg.FieldSchema, pkg.CollectionSchema
+    assert (DataType.INT64, DataType.VARCHAR, DataType.JSON, DataType.FLOAT_VECTOR) == (5, 21, 23, 101)
+    # exactly the construction of /root/reference/milvus/insert_embeddings.py:52-60
+    fields = [FieldSchema(name="id", dtype=DataType.INT64, is_primary=True, auto_id=True),
+              FieldSchema(name="file_id", dtype=DataType.VARCHAR, max_length=500),
+              FieldSchema(name="vector", dtype=DataType.FLOAT_VECTOR, dim=6144),
+              FieldSchema(name="text", dtype=DataType.VARCHAR, max_length=1000)]
+    schema = CollectionSchema(fields, description="Embeddings and Biographies Collection", metric_type="COSINE")
+    schema.verify()
+    assert schema.primary_field.name == "id" and schema.vector_field.dim == 6144 and schema.metric_type == "COSINE"
+    with pytest.raises(pkg.MilvusException):
+        CollectionSchema([FieldSchema("v", DataType.FLOAT_VECTOR, dim=4)]).verify()
+
+
+def test_collection_management_and_errors(pkg, tmp_path):
+    c = pkg.MilvusClient(str(tmp_path / "a.db"))
+    assert not c.has_collection(collection_name="x")
+    c.create_collection(collection_name="x", dimension=8)
+    assert c.has_collection("x") and c.list_collections() == ["x"]
+    d = c.describe_collection("x")
+    assert d["metric_type"] == "COSINE" and d["enable_dynamic_field"] and d["fields"][1]["params"]["dim"] == 8
+    with pytest.raises(pkg.MilvusException):
+        c.create_collection("x", dimension=8)
+    with pytest.raises(pkg.MilvusException):
+        c.search("nope", data=[[0.0] * 8])
+    with pytest.raises(pkg.MilvusException):
+        c.search("x", data=[[0.0] * 7], limit=3)                          # dimension mismatch
+    with pytest.raises(pkg.MilvusException):
+        c.search("x", data=[[0.0] * 8], limit=0)
+    with pytest.raises(pkg.MilvusException):
+        c.search("x", data=[[0.0] * 8], metric_type="L2")
+    with pytest.raises(pkg.MilvusException):
+        c.insert("x", [{"id": 1, "vector": [0.0] * 9}])
+    with pytest.raises(pkg.MilvusException):
+        c.insert("x", [{"vector": [0.0] * 8}])                            # pk missing, auto_id off
+    # the reference's tolerated kwargs on an empty collection
+    assert c.search(collection_name="x", data=[[0.0] * 8], anns_field="vector", param={"nprobe": 10}, limit=3,
+                    output_fields=["file_id", "text"], filter=None) == [[]]
+    c.create_index(collection_name="x", field_name="vector", index_params={"index_type": "IVF_FLAT", "params": {"nlist": 128}})
+    c.drop_collection(collection_name="x")
+    assert not c.has_collection("x")
+    c.close()
+    # a fresh client on the same file sees the (now empty) catalogue
+    assert pkg.MilvusClient(str(tmp_path / "a.db")).list_collections() == []
+    with pytest.raises(pkg.MilvusException):
+        pkg.MilvusClient("not_a_db_path.txt")
+
+
+def test_milvus_lite_file_roundtrip_and_oracle_decoder(tmp_path):
+    """Product-side writer -> product-side reader AND the oracle's independent decoder."""
+    mldb = load_pkg("milvus_lite_db")
+    from oracle import milvus_db as odb
+    path = str(tmp_path / "rt.db")
+    f = mldb.MilvusLiteFile(path)
+    fields = [{"name": "id", "dtype": 5, "is_primary": True}, {"name": "vector", "dtype": 101, "dim": 6}]
+    f.create_collection("c", fields, enable_dynamic=True)
+    f.write_index("c", 101, "vector", {"index_type": "AUTOINDEX", "metric_type": "COSINE", "dim": 6})
+    rng = np.random.default_rng(0)
+    vec = rng.standard_normal((5, 6)).astype(np.float32)
+    rows = [{"id": i - 2, "vector": vec[i]} for i in range(5)]
+    dyn = [{"file_id": f"f{i}.wav", "text": "héllo 你好 %d" % i} for i in range(5)]
+    f.append("c", fields, "id", rows, dyn)
+    f.close()
+    g = mldb.MilvusLiteFile(path)
+    schema, index = g.read_meta("c")
+    assert [x["name"] for x in schema["fields"]] == ["id", "vector", "$meta"] and schema["enable_dynamic_field"]
+    assert index["metric_type"] == "COSINE" and index["dim"] == "6"
+    back = g.load_rows("c")
+    assert [r["id"] for r in back] == [-2, -1, 0, 1, 2]
+    assert all(np.array_equal(r["vector"], vec[i]) for i, r in enumerate(back))
+    assert back[3]["$meta"] == dyn[3]
+    pks, X, meta = odb.load_collection(path, "c")
+    assert pks.tolist() == [-2, -1, 0, 1, 2] and np.array_equal(X, vec) and meta[4] == dyn[4]
+    assert odb.list_collections(path) == ["c"]
+
+
+def test_synth_generator_properties():
+    synth = load_pkg("synth")
+    a = synth.synth_rows(42, 1000, 64, 768)
+    b = synth.synth_rows(42, 1032, 32, 768)
+    assert np.array_equal(a[32:], b)                                     # pure function of (seed, row)
+    assert np.allclose(np.linalg.norm(a.astype(np.float64), axis=1), 1.0, atol=1e-6)
+    assert not np.array_equal(a[0], synth.synth_rows(43, 1000, 1, 768)[0])
+    g = a @ a.T
+    off = g[~np.eye(64, dtype=bool)]
+    assert abs(off.mean()) < 0.01 and 0.02 < off.std() < 0.05            # ~N(0, 1/768) cosines
+    q = synth.planted_queries(43, 42, 5000, 40, 768)
+    assert q.shape == (40, 768) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
+
+
+def test_shard_range_matches_oracle():
+    sh = load_pkg("sharded")
+    from oracle import flat_search as fs
+    for n, w in [(10, 4), (2, 4), (0, 2), (1_000_000, 8), (100_000_001, 8)]:
+        assert [sh.shard_range(n, r, w) for r in range(w)] == fs.shard_bounds(n, w)
+    with pytest.raises(ValueError):
+        sh.shard_range(10, 4, 4)

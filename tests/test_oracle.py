@@ -1,0 +1,168 @@
+"""CPU suite: the oracle against the golden vectors recovered from the reference's shipped
+artefacts, its two independent restatements against each other, and its algebraic properties."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from conftest import GOLDEN, ROOT
+from oracle import flat_search as fs
+
+
+def test_kat1_self_query_top1(f1):
+    """/root/reference/milvus/RAG.py:567-582: every stored vector retrieves itself, distance ~1."""
+    X = f1["X"]
+    ids, dist, rows = fs.search(X, np.arange(130), X, 1, "COSINE")
+    assert np.array_equal(rows[:, 0], np.arange(130))
+    assert np.all(np.abs(dist[:, 0] - 1.0) <= 1e-6)
+
+
+def test_kat2_top5_golden_and_variants(f1):
+    X, kat = f1["X"], f1["kat"]
+    ids, dist, rows = fs.search(X, np.arange(130), X, 5, "COSINE")
+    assert np.array_equal(rows, kat["self_rows"])
+    assert np.array_equal(dist, kat["self_dist"])
+    for variant in ("normalize_then_dot", "dot_then_divide"):
+        _, d32, r32 = fs.search(X, np.arange(130), X, 5, "COSINE", accum="f32", variant=variant)
+        assert np.array_equal(r32, kat["self_rows"])
+        assert np.allclose(d32, kat["self_dist"], rtol=1e-5, atol=0)
+
+
+def test_c1_perturbed_queries_golden(f1):
+    X, kat = f1["X"], f1["kat"]
+    _, dist, rows = fs.search(X, np.arange(130), kat["pert_queries"], 5, "COSINE")
+    assert np.array_equal(rows, kat["pert_rows"])
+    assert np.array_equal(rows[:, 0], kat["pert_pick"])
+    assert np.array_equal(dist, kat["pert_dist"])
+    _, dip, rip = fs.search(X, np.arange(130), kat["pert_queries"], 5, "IP")
+    assert np.array_equal(rip, kat["pert_ip_rows"]) and np.array_equal(dip, kat["pert_ip_dist"])
+
+
+def test_f1_shape_and_duplicate_pks(f1):
+    assert f1["X"].shape == (130, 6144)
+    nrm = np.linalg.norm(f1["X"], axis=1)
+    assert 35.0 < nrm.min() and nrm.max() < 43.5           # stored un-normalised
+    assert len(set(f1["pks"].tolist())) == 21               # pks restart per speaker (RAG.py:507)
+    assert all(set(m) == {"file_id", "text"} for m in f1["meta"])
+    ids, _, rows = fs.search(f1["X"], f1["pks"], f1["X"], 5, "COSINE")
+    assert np.array_equal(ids, f1["kat"]["self_pk_ids"])
+    # dedup_pk keeps one hit per primary key
+    ids_d, _, _ = fs.search(f1["X"], f1["pks"], f1["X"][:8], 5, "COSINE", dedup_pk=True)
+    assert all(len(set(r.tolist())) == 5 for r in ids_d)
+
+
+def test_f2_output_schema_pinned(f1):
+    """output_emb/search_results.json: distance is a similarity in (0.8, 0.95), ids exist in F1."""
+    with open(os.path.join(GOLDEN, "f2_search_results_schema.json"), encoding="utf-8") as f:
+        f2 = json.load(f)
+    assert f2["keys"] == ["distance", "retrieved_file_id", "retrieved_text", "speaker", "whisper", "zh_text"]
+    assert 0.81 < f2["distance_min"] < f2["distance_max"] < 0.95
+    assert f2["all_retrieved_in_f1"] and f2["n_rows"] == 64
+
+
+def test_ties_break_by_id_and_padding():
+    X = np.array([[1, 0], [1, 0], [0, 1], [2, 0]], dtype=np.float32)
+    ids = np.array([7, 3, 9, 5])
+    out_ids, dist, rows = fs.search(X, ids, np.array([[1, 0]], np.float32), 6, "COSINE")
+    assert out_ids[0].tolist() == [3, 5, 7, 9, -1, -1]      # three exact ties at 1.0 -> id order
+    assert dist[0, 3] == 0.0 and np.isneginf(dist[0, 4])
+    out_ids, dist, _ = fs.search(X, ids, np.array([[1, 0]], np.float32), 2, "IP")
+    assert out_ids[0].tolist() == [5, 3] and dist[0].tolist() == [2.0, 1.0]
+    e_ids, e_d, _ = fs.search(np.zeros((0, 2), np.float32), np.zeros(0, np.int64), np.ones((2, 2), np.float32), 3)
+    assert np.all(e_ids == -1) and np.all(np.isneginf(e_d))
+    with pytest.raises(ValueError):
+        fs.search(X, ids, np.ones((1, 3), np.float32), 1)
+
+
+def _c_oracle():
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle_flat.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    lib = ctypes.CDLL(so)
+    lib.oracle_flat_search.restype = ctypes.c_int
+    return lib
+
+
+@pytest.mark.parametrize("metric", ["COSINE", "IP"])
+def test_c_restatement_agrees_with_numpy(metric):
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((700, 96)).astype(np.float32) * rng.uniform(0.5, 3, (700, 1)).astype(np.float32)
+    X[100] = X[50]                                           # exact duplicate -> id tie-break
+    ids = rng.permutation(700).astype(np.int64)
+    Q = rng.standard_normal((9, 96)).astype(np.float32)
+    Q[0] = X[50]
+    k = 12
+    e_ids, e_d, _ = fs.search(X, ids, Q, k, metric)
+    lib = _c_oracle()
+    o_ids = np.empty((9, k), np.int64)
+    o_d = np.empty((9, k), np.float32)
+    rc = lib.oracle_flat_search(X.ctypes.data_as(ctypes.c_void_p), ids.ctypes.data_as(ctypes.c_void_p),
+                                ctypes.c_int64(700), 96, Q.ctypes.data_as(ctypes.c_void_p), 9, k,
+                                0 if metric == "COSINE" else 1, o_ids.ctypes.data_as(ctypes.c_void_p),
+                                o_d.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    assert np.array_equal(o_ids, e_ids)
+    assert np.allclose(o_d, e_d, rtol=1e-6, atol=1e-7)
+
+
+def test_search_large_equals_search():
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((5000, 64)).astype(np.float32)
+    Q = rng.standard_normal((5, 64)).astype(np.float32)
+    ids = np.arange(5000) * 3
+    a = fs.search(X, ids, Q, 10, "COSINE")
+    b = fs.search_large(X, ids, Q, 10, "COSINE")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 60), st.integers(1, 5), st.integers(1, 12), st.integers(0, 10_000), st.sampled_from(["COSINE", "IP"]))
+def test_property_shard_merge_equals_global(n, world, k, seed, metric):
+    """top-k is decomposable: merge of per-shard top-k == global top-k."""
+    rng = np.random.default_rng(seed)
+    X = np.round(rng.standard_normal((n, 8)) * 2).astype(np.float32)    # coarse grid -> many ties
+    ids = rng.permutation(n).astype(np.int64)
+    Q = np.round(rng.standard_normal((3, 8)) * 2).astype(np.float32)
+    g_ids, g_d, _ = fs.search(X, ids, Q, k, metric)
+    parts = []
+    for lo, hi in fs.shard_bounds(n, world):
+        p_ids, _, p_rows = fs.search(X[lo:hi], ids[lo:hi], Q, k, metric)
+        s64 = np.full(p_ids.shape, -np.inf)
+        for i in range(3):
+            xn = None
+            s = fs.scores64(X[lo:hi], Q[i], metric, xn) if hi > lo else np.zeros(0)
+            valid = p_rows[i] >= 0
+            s64[i, valid] = s[p_rows[i][valid]]
+        parts.append((p_ids, s64))
+    m_ids, m_s = fs.merge_shards(parts, k)
+    assert np.array_equal(m_ids, g_ids)
+    assert np.array_equal(m_s.astype(np.float32), g_d)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(2, 80), st.integers(1, 10), st.integers(0, 10_000))
+def test_property_invariances(n, k, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, 16)).astype(np.float32)
+    ids = np.arange(n, dtype=np.int64)
+    q = rng.standard_normal((1, 16)).astype(np.float32)
+    base = fs.search(X, ids, q, k, "COSINE")
+    # cosine ignores positive rescaling of rows by powers of two (exact in fp32) and of the query
+    scale = (2.0 ** rng.integers(-3, 4, size=(n, 1))).astype(np.float32)
+    assert np.array_equal(fs.search(X * scale, ids, q * 4, k, "COSINE")[0], base[0])
+    # permuting the rows (ids travel with them) does not change the answer
+    perm = rng.permutation(n)
+    assert np.array_equal(fs.search(X[perm], ids[perm], q, k, "COSINE")[0], base[0])
+    # scores are sorted best-first and bounded
+    d = base[1][0][: min(k, n)]
+    assert np.all(np.diff(d) <= 0) and np.all(np.abs(d) <= 1 + 1e-6)
+
+
+def test_shard_bounds():
+    assert fs.shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert fs.shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert fs.shard_bounds(0, 2) == [(0, 0), (0, 0)]
