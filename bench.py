@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark: queries/sec of exact top-10 cosine search on BASELINE.json configs[1]
+(1M x 768 synthetic unit-norm embeddings, batch 1024 and batch 1) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--rows R] [--dim D] [--k K]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference     # the reference's CPU path (FLAT search restated; oracle/)
+
+One JSON line on stdout (rank 0).  `value` = whole-job QPS with queries already resident in HBM;
+`e2e` = the same through the C-ABI host call (pinned host buffers, H2D + D2H inside the timed
+region); `roofline` = the dominant scan kernel timed with CUDA events on its launch stream;
+`cpu_baseline` = the oracle's CPU path on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec top-10 exact search"
+SEED_DB, SEED_Q = 42, 43
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--metric", default="COSINE")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-path", type=int, default=0, help="0 auto, 1 gemv, 2 gemm")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"C2: {a.rows} x {a.dim} synthetic unit-norm rows, {a.metric} top-{a.k}, batch {a.batch} (and batch 1)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if not any(lo - 0.05 <= t <= hi + 0.05 for lo, hi in windows):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's CPU path (numpy fp32 BLAS FLAT search)
+# ------------------------------------------------------------------------------------------------
+def host_rows(a, lo, hi):
+    synth = importlib.import_module("autostyle-tts_b200.synth")
+    out = np.empty((hi - lo, a.dim), dtype=np.float32)
+    for s in range(lo, hi, 65536):
+        e = min(hi, s + 65536)
+        out[s - lo:e - lo] = synth.synth_rows(SEED_DB, s, e - s, a.dim)
+    return out
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_flat_time(Xn, Q, k, reps=1):
+    from oracle import flat_search as fs
+    fs.cpu_flat_baseline(Xn[:65536], Q[:2], k)        # BLAS warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fs.cpu_flat_baseline(Xn, Q, k)
+    return (time.perf_counter() - t0) / reps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    synth = importlib.import_module("autostyle-tts_b200.synth")
+    X = host_rows(a, 0, a.rows)                        # unit-norm rows: the cached FLAT/cosine index content
+    nq = min(a.batch, 64)                              # bounded sample of the batch per step
+    Q = synth.planted_queries(SEED_Q, SEED_DB, a.rows, a.batch, a.dim)[:nq]
+    steps, warm = max(1, min(a.steps, 10)), max(1, min(a.warmup, 2))
+    from oracle import flat_search as fs
+    for _ in range(warm):
+        fs.cpu_flat_baseline(X, Q, a.k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fs.cpu_flat_baseline(X, Q, a.k)
+    dt = (time.perf_counter() - t0) / steps
+    qps = nq / dt
+    sample = f"{nq} of {a.batch} queries x all {a.rows} rows per step, fp32 OpenBLAS sgemm + argpartition"
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim,
+                                                              "k": a.k, "batch": a.batch},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("autostyle-tts_b200")
+    synth = importlib.import_module("autostyle-tts_b200.synth")
+    sharded = importlib.import_module("autostyle-tts_b200.sharded")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops", 1590.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    ss = sharded.ShardedStore(a.dim, a.metric, a.rows, rank, world, device=local)
+    st = ss.store
+    ss.fill_synthetic(SEED_DB)
+    st.set_option("scan_path", a.scan_path)
+    torch.cuda.synchronize()
+    rows_local = len(st)
+    dpad = (a.dim + 63) // 64 * 64
+
+    Qh = synth.planted_queries(SEED_Q, SEED_DB, a.rows, max(a.batch, 1), a.dim)
+    q_pinned = torch.from_numpy(Qh).pin_memory()
+    q_dev = q_pinned.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_lo = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t_hi = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (t_lo, t_hi)
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    windows = []
+    results = {}
+    for batch in sorted({a.batch, 1}, reverse=True):
+        q = q_dev[:batch]
+        qh = q_pinned[:batch].numpy()
+        fn_dev = (lambda: ss.search(q, a.k))
+        # device-resident throughput + live roofline of the dominant scan kernel
+        st.scan_timing(1)
+        l0 = st.stat("kernel_launches")
+        ms, win = timed(fn_dev, a.steps, a.warmup)
+        launches = (st.stat("kernel_launches") - l0) // (a.steps + a.warmup) * a.steps
+        scan_ms, scan_n = st.scan_timing(0)
+        windows.append(win)
+        path, levels = st.stat("last_scan_path"), st.stat("last_levels")
+        # rows the final level visits = all groups minus those sampled by the sparser levels
+        groups = (rows_local + 255) // 256
+        sampled = (groups + 31) // 32 if levels > 1 else 0
+        rows_final = min(rows_local, (groups - sampled) * 256)
+        if path == 2:
+            work = 2.0 * batch * rows_final * dpad
+            roof = {"bound": "tensor", "achieved": work / (scan_ms * 1e-3) / 1e12 if scan_ms else None, "peak": tc_peak,
+                    "unit": "TFLOP/s"}
+        else:
+            passes = (batch + 7) // 8
+            work = float(passes) * rows_final * dpad * 2
+            roof = {"bound": "hbm", "achieved": work / (scan_ms * 1e-3) / 1e9 if scan_ms else None, "peak": hbm_peak,
+                    "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+        roof.update({"traffic": None, "peak_source": peak_src, "kernel": "scan_gemm (tcgen05)" if path == 2 else "scan_gemv",
+                     "kernel_ms": scan_ms, "timed_launch_groups": scan_n, "algorithmic_work_per_launch_group": work})
+        # end to end through the C-ABI host call (single GPU): pinned host queries in, host hits out
+        e2e = None
+        if world == 1:
+            fn_host = (lambda: st.search(qh, a.k))
+            ms_e, win_e = timed(fn_host, a.steps, a.warmup)
+            windows.append(win_e)
+            e2e = {"value": batch / (ms_e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e,
+                   "h2d_bytes_per_step": int(batch * a.dim * 4), "d2h_bytes_per_step": int(batch * a.k * 20),
+                   "api": "avs_search_host (C-ABI, host buffers)"}
+        else:
+            def fn_host_sharded():
+                qd = q_pinned[:batch].cuda(non_blocking=True)
+                ids, sc = ss.search(qd, a.k)
+                return ids.cpu(), sc.cpu()
+            ms_e, win_e = timed(fn_host_sharded, a.steps, a.warmup)
+            windows.append(win_e)
+            e2e = {"value": batch / (ms_e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e,
+                   "h2d_bytes_per_step": int(batch * a.dim * 4), "d2h_bytes_per_step": int(batch * a.k * 12),
+                   "api": "avs_search_sharded (pinned H2D, D2H of ids+scores)"}
+        results[batch] = {"qps": batch / (ms * 1e-3), "ms": ms, "launches": int(launches), "roofline": roof, "e2e": e2e,
+                          "scan_path": path, "levels": levels, "kprime": st.stat("last_kprime")}
+    unc = st.stat("uncertified_queries")
+    rep = st.stat("repaired_queries")
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        X = np.concatenate([st.get_rows(lo, min(131072, rows_local - lo)) for lo in range(0, rows_local, 131072)])
+        nq_cpu = min(a.batch, 128)
+        dt = cpu_flat_time(X, Qh[:nq_cpu], a.k)
+        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
+               "sample": f"{nq_cpu} of {a.batch} queries x all {rows_local} rows, one pass ({dt:.2f} s), numpy fp32 sgemm + argpartition"}
+        dt1 = cpu_flat_time(X, Qh[:1], a.k, reps=3)
+        cpu["batch1_value"] = 1.0 / dt1
+        # parity spot-check of the bench workload itself against the float64 oracle
+        from oracle import flat_search as fs
+        exp_ids, _, _ = fs.search_large(X, np.arange(rows_local), Qh[:8], a.k, a.metric)
+        got_ids, _ = st.search(Qh[:8], a.k)
+        cpu["parity_ids_match_oracle"] = bool(np.array_equal(got_ids, exp_ids))
+        del X
+
+    if rank == 0:
+        clk = clocks.stop(windows)
+        main = results[a.batch]
+        line = {"metric": METRIC, "value": main["qps"], "unit": "queries/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": main["ms"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
+                           "metric_type": a.metric, "sharding": f"rows/{world}" if world > 1 else "none",
+                           "l2_policy": f"inputs larger than L2: the scan streams {rows_local * dpad * 2 / 1e6:.0f} MB of bf16 rows per step (L2 126 MB)",
+                           "arith": "bf16 operands, fp32 accumulate scan; float64 rescoring of the candidates",
+                           "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],
+                           "oversample_kprime": main["kprime"]},
+                "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
+                "cpu_baseline": cpu, "uncertified_queries": unc, "repaired_queries": rep}
+        if 1 in results and a.batch != 1:
+            b1 = results[1]
+            line["batch1"] = {"value": b1["qps"], "unit": "queries/s", "ms_per_step": b1["ms"], "e2e": b1["e2e"],
+                              "gpu_launches": b1["launches"], "roofline": b1["roofline"]}
+        print(json.dumps(line), flush=True)
+    ss.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

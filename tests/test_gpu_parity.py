@@ -1,0 +1,287 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI (ctypes -> libavs.so), against the
+oracle on the same seeded inputs and against the golden fixtures recovered from the reference.
+
+Bar (BASELINE.json north_star): identical top-k id list (ties broken by id), scores within 1e-5
+relative.  Tolerance used below: ids exact, |score - oracle| <= 1e-5 * max(1, |oracle|)  — the
+CUDA rescoring is float64 like the oracle, so the observed difference is the final fp32 rounding.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_pkg
+from oracle import flat_search as fs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _check(got_ids, got_d, exp_ids, exp_d):
+    got_ids, got_d = np.asarray(got_ids), np.asarray(got_d)
+    assert np.array_equal(got_ids, exp_ids), f"id lists differ at {np.argwhere(got_ids != exp_ids)[:5]}"
+    fin = np.isfinite(exp_d)
+    assert np.array_equal(np.isfinite(got_d), fin)
+    assert np.all(np.abs(got_d[fin] - exp_d[fin]) <= RTOL * np.maximum(1.0, np.abs(exp_d[fin])))
+
+
+def _data(n, d, nq, seed, scale=True):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    if scale:
+        X *= rng.uniform(0.2, 40.0, (n, 1)).astype(np.float32)          # un-normalised, like the reference's rows
+    Q = rng.standard_normal((nq, d)).astype(np.float32) * 7.0
+    if n:
+        pick = rng.integers(0, n, size=max(1, nq // 3))
+        Q[: pick.size] = X[pick] + 0.05 * rng.standard_normal((pick.size, d)).astype(np.float32)
+    ids = rng.permutation(max(n, 1))[:n].astype(np.int64) * 3 - 17
+    return X, ids, Q
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = load_pkg()
+    p.load_library()
+    return p
+
+
+@pytest.mark.parametrize("metric", ["COSINE", "IP"])
+@pytest.mark.parametrize("n,d,nq,k", [(130, 6144, 5, 5), (1000, 768, 1, 10), (5000, 768, 8, 10), (3000, 100, 3, 1),
+                                      (777, 64, 2, 50), (20000, 1024, 4, 100), (257, 8, 7, 10), (4096, 3072, 2, 50)])
+def test_store_matches_oracle(pkg, metric, n, d, nq, k):
+    X, ids, Q = _data(n, d, nq, seed=n + d + k)
+    st = pkg.Store(d, metric, capacity=n)
+    try:
+        st.insert(X, ids)
+        assert len(st) == n
+        got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
+        exp_ids, exp_d, exp_rows = fs.search(X, ids, Q, k, metric)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert np.array_equal(got_rows, exp_rows)
+        assert st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
+
+
+def test_multi_level_scan_and_device_tensor_api(pkg):
+    """N large enough for three sampling levels; torch CUDA tensors in, device tensors out."""
+    import torch
+    n, d, nq, k = 300_000, 128, 6, 10
+    X, ids, Q = _data(n, d, nq, seed=9, scale=False)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(torch.from_numpy(X).cuda(), torch.from_numpy(ids).cuda())
+        got_ids, got_d = st.search(torch.from_numpy(Q).cuda(), k)
+        assert got_ids.is_cuda and got_d.dtype == torch.float32
+        assert st.stat("last_levels") >= 2
+        exp_ids, exp_d, _ = fs.search_large(X, ids, Q, k, "COSINE")
+        _check(got_ids.cpu().numpy(), got_d.cpu().numpy(), exp_ids, exp_d)
+        assert st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
+
+
+def test_query_batches_larger_than_one_pass(pkg):
+    n, d, nq, k = 6000, 256, 37, 10
+    X, ids, Q = _data(n, d, nq, seed=21)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        got_ids, got_d = st.search(Q, k)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, k, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+    finally:
+        st.close()
+
+
+def test_edge_cases_empty_ragged_ties(pkg):
+    st = pkg.Store(16, "COSINE", capacity=0)
+    try:
+        ids, d = st.search(np.ones((2, 16), np.float32), 4)                 # empty store -> padding
+        assert np.all(ids == -1) and np.all(np.isneginf(d))
+        rng = np.random.default_rng(3)
+        X = rng.standard_normal((40, 16)).astype(np.float32)
+        X[10] = X[5]; X[30] = X[5] * 2.0                                     # exact cosine ties (power-of-two scale)
+        X[7] = 0.0                                                          # zero row scores 0
+        pk = np.arange(40, dtype=np.int64)[::-1].copy()                     # ids descending: tie order != row order
+        st.insert(X[:25], pk[:25])                                          # ragged: two inserts, growth past capacity
+        st.insert(X[25:], pk[25:])
+        Q = np.stack([X[5], rng.standard_normal(16).astype(np.float32)])
+        got_ids, got_d = st.search(Q, 64)                                   # k > N -> N hits then padding
+        exp_ids, exp_d, _ = fs.search(X, pk, Q, 64, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert got_ids[0, :3].tolist() == sorted([int(pk[5]), int(pk[10]), int(pk[30])])
+        with pytest.raises(pkg.AvsError):
+            st.search(np.ones((1, 15), np.float32), 4)
+        with pytest.raises(pkg.AvsError):
+            st.search(np.ones((1, 16), np.float32), 0)
+        with pytest.raises(pkg.AvsError):
+            st.search(np.ones((1, 16), np.float32), 257)
+    finally:
+        st.close()
+
+
+def test_repair_path_is_exact(pkg):
+    """Force the certificate to fail (forced flag, and a starved candidate list): the float64
+    repair scan must still return the oracle's answer."""
+    n, d, nq, k = 9000, 192, 5, 10
+    X, ids, Q = _data(n, d, nq, seed=77)
+    exp_ids, exp_d, _ = fs.search(X, ids, Q, k, "COSINE")
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        st.set_option("force_repair", 1)
+        got_ids, got_d = st.search(Q, k)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert st.stat("repaired_queries") == nq
+        st.set_option("force_repair", 0)
+        # near-duplicate cluster wider than the candidate list: 40 rows within 1e-4 of each other
+        base = X[123].copy()
+        Xc = X.copy()
+        for j in range(40):
+            Xc[2000 + j] = base * (1.0 + 0.01 * j) + 1e-4 * np.random.default_rng(j).standard_normal(d).astype(np.float32)
+        st2 = pkg.Store(d, "COSINE", capacity=n)
+        st2.insert(Xc, ids)
+        st2.set_option("oversample", 16)
+        q = base[None, :]
+        g_ids, g_d = st2.search(q, 16)
+        e_ids, e_d, _ = fs.search(Xc, ids, q, 16, "COSINE")
+        _check(g_ids, g_d, e_ids, e_d)
+        assert st2.stat("uncertified_queries") == 0
+        st2.close()
+    finally:
+        st.close()
+
+
+def test_golden_f1_through_the_milvus_client(pkg, f1, tmp_path):
+    """C1: the reference's own database through the reference's own call shapes."""
+    X, pks, meta, kat = f1["X"], f1["pks"], f1["meta"], f1["kat"]
+    client = pkg.MilvusClient(str(tmp_path / "milvus_demo.db"))
+    name = "embeddings_biographies_collection"
+    if client.has_collection(collection_name=name):
+        client.drop_collection(collection_name=name)
+    client.create_collection(collection_name=name, dimension=6144)         # RAG.py:54-57
+    data = [{"id": int(pks[i]), "file_id": meta[i]["file_id"], "vector": X[i].tolist(), "text": meta[i]["text"]}
+            for i in range(130)]                                             # RAG.py:506-511
+    res = client.insert(collection_name=name, data=data)
+    assert res["insert_count"] == 130
+    # KAT-1 (RAG.py:567-582): top-1 self query, printed id/distance/entity
+    for i in (0, 17, 64, 129):
+        r = client.search(collection_name=name, data=[X[i].tolist()], limit=1, filter=None,
+                          output_fields=["file_id", "text"])
+        top = r[0][0]
+        assert top["entity"]["file_id"] == meta[i]["file_id"] and top["entity"]["text"] == meta[i]["text"]
+        assert top.get("id") == int(pks[i]) and abs(top.get("distance") - 1.0) <= 1e-6
+    # KAT-2: top-5 for all 130 self-queries in one batch, search_embeddings.py kwargs
+    r = client.search(collection_name=name, data=list(X), anns_field="vector", param={"nprobe": 10}, limit=5,
+                      output_fields=["file_id", "text"])
+    assert len(r) == 130 and all(len(h) == 5 for h in r)
+    got_rows = np.array([[next(j for j in range(130) if meta[j]["file_id"] == hit["entity"]["file_id"]) for hit in hits]
+                         for hits in r])
+    assert np.array_equal(got_rows, kat["self_rows"])
+    got_d = np.array([[hit["distance"] for hit in hits] for hits in r], dtype=np.float32)
+    assert np.all(np.abs(got_d - kat["self_dist"]) <= RTOL)
+    assert np.array_equal(np.array([[hit["id"] for hit in hits] for hits in r]), kat["self_pk_ids"])
+    # C1 perturbed queries, explicit metric (src/search_milvus.py:139-146)
+    r = client.search(collection_name=name, data=kat["pert_queries"], anns_field="vector", metric_type="COSINE",
+                      limit=5, output_fields=["file_id"])
+    got_rows = np.array([[next(j for j in range(130) if meta[j]["file_id"] == hit["entity"]["file_id"]) for hit in hits]
+                         for hits in r])
+    assert np.array_equal(got_rows, kat["pert_rows"])
+    with open(os.path.join(GOLDEN, "f2_search_results_schema.json"), encoding="utf-8") as f:
+        f2 = json.load(f)
+    assert 0.5 < min(h[0]["distance"] for h in r) <= 1.0 and f2["distance_max"] < 1.0
+    client.close()
+    # a second process re-opens the file (search_embeddings.py:31) and finds the collection
+    again = pkg.MilvusClient(str(tmp_path / "milvus_demo.db"))
+    assert again.has_collection(name) and again.get_collection_stats(name)["row_count"] == 130
+    top = again.search(name, data=[X[3]], limit=3, output_fields=["file_id", "text"])[0]
+    assert [h["entity"]["file_id"] for h in top] == [meta[j]["file_id"] for j in kat["self_rows"][3][:3]]
+    # dedup_pk policy: one hit per primary key
+    dd = pkg.MilvusClient(str(tmp_path / "milvus_demo.db"), dedup_pk=True)
+    hits = dd.search(name, data=[X[0]], limit=5)[0]
+    assert len({h["id"] for h in hits}) == 5
+    exp_ids, _, _ = fs.search(X, pks, X[:1], 5, "COSINE", dedup_pk=True)
+    assert [h["id"] for h in hits] == exp_ids[0].tolist()
+    again.close(); dd.close()
+
+
+def test_schema_variant_auto_id_and_ip(pkg):
+    """insert_embeddings.py:52-79: explicit schema, auto_id, IVF_FLAT index request, no dynamic fields."""
+    DataType, FieldSchema, CollectionSchema = pkg.DataType, pkg.FieldSchema, pkg.CollectionSchema
+    c = pkg.MilvusClient(":memory:")
+    schema = CollectionSchema([FieldSchema(name="id", dtype=DataType.INT64, is_primary=True, auto_id=True),
+                               FieldSchema(name="file_id", dtype=DataType.VARCHAR, max_length=500),
+                               FieldSchema(name="vector", dtype=DataType.FLOAT_VECTOR, dim=32),
+                               FieldSchema(name="text", dtype=DataType.VARCHAR, max_length=1000)],
+                              description="x", metric_type="COSINE")
+    c.create_collection(collection_name="s", schema=schema)
+    c.create_index(collection_name="s", field_name="vector", index_params={"index_type": "IVF_FLAT", "params": {"nlist": 128}})
+    rng = np.random.default_rng(1)
+    V = rng.standard_normal((50, 32)).astype(np.float32)
+    res = c.insert(collection_name="s", data=[{"file_id": f"f{i}", "vector": V[i].tolist(), "text": f"t{i}"} for i in range(50)])
+    assert res["ids"] == list(range(1, 51))
+    hits = c.search("s", data=[V[7].tolist()], limit=3, output_fields=["file_id"])[0]
+    exp_ids, exp_d, _ = fs.search(V, np.arange(1, 51), V[7:8], 3, "COSINE")
+    assert [h["id"] for h in hits] == exp_ids[0].tolist() and hits[0]["entity"] == {"file_id": "f7"}
+    with pytest.raises(pkg.MilvusException):
+        c.insert("s", [{"file_id": "a", "vector": V[0].tolist(), "text": "b", "extra": 1}])   # no dynamic fields
+    # IP collection through index_params
+    c.create_collection("ip", dimension=32, metric_type="IP")
+    c.insert("ip", [{"id": i, "vector": V[i]} for i in range(50)])
+    hits = c.search("ip", data=[V[7]], limit=4)[0]
+    exp_ids, exp_d, _ = fs.search(V, np.arange(50), V[7:8], 4, "IP")
+    assert [h["id"] for h in hits] == exp_ids[0].tolist()
+    assert np.allclose([h["distance"] for h in hits], exp_d[0], rtol=RTOL)
+    ids_t, d_t = c.search_tensors("ip", V[:5], limit=4)
+    assert np.array_equal(ids_t, fs.search(V, np.arange(50), V[:5], 4, "IP")[0])
+    c.close()
+
+
+def test_synthetic_fill_is_replayable_and_full_size_config(pkg):
+    """C2 at full size: 1M x 768 generated on device, rows bit-identical to the host replay, and the
+    search equal to the oracle on a query sample (planted neighbours included)."""
+    synth = load_pkg("synth")
+    n, d, k = 1_000_000, 768, 10
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.fill_synthetic(42, 0, n)
+        assert len(st) == n
+        for lo in (0, 499_999, n - 64):
+            assert np.array_equal(st.get_rows(lo, 64), synth.synth_rows(42, lo, 64, d))
+        assert np.array_equal(st.get_ids(n - 5, 5), np.arange(n - 5, n))
+        Q = synth.planted_queries(43, 42, n, 16, d)
+        got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
+        assert st.stat("uncertified_queries") == 0
+        X = np.concatenate([st.get_rows(lo, 100_000) for lo in range(0, n, 100_000)])
+        exp_ids, exp_d, exp_rows = fs.search_large(X, np.arange(n), Q, k, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+        # size-independent properties: sorted best-first, self-consistent, idempotent
+        assert np.all(np.diff(got_d, axis=1) <= 0)
+        again_ids, again_d = st.search(Q, k)
+        assert np.array_equal(again_ids, got_ids) and np.array_equal(again_d, got_d)
+        top1_ids, _ = st.search(X[got_rows[:, 0]], 1)                         # a hit queried back retrieves itself
+        assert np.array_equal(top1_ids[:, 0], got_ids[:, 0])
+    finally:
+        st.close()
+
+
+def test_two_gpu_sharded_search(pkg):
+    """World-size-2 NCCL path in ONE process is not possible with one comm per process; the real
+    multi-rank check runs under torchrun in tests/dist_gpu_check.py (invoked by hand / bench).  Here:
+    a single-rank communicator exercises pack -> ncclAllGather -> merge against the plain search."""
+    import torch
+    n, d, nq, k = 5000, 128, 9, 10
+    X, ids, Q = _data(n, d, nq, seed=5)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        st.comm_init(pkg.Store.nccl_unique_id(), 0, 1)
+        q = torch.from_numpy(Q).cuda()
+        a_ids, a_d = st.search(q, k, sharded=True)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, k, "COSINE")
+        _check(a_ids.cpu().numpy(), a_d.cpu().numpy(), exp_ids, exp_d)
+    finally:
+        st.close()
