@@ -127,7 +127,8 @@ struct avs_store {
     AvsScratch sc;
     int num_sms = 148;
     // options
-    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 1 << 30, opt_ratio = 32, opt_force_repair = 0;
+    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 9, opt_ratio = 32, opt_force_repair = 0,
+        opt_cta_group = 2;
     // stats
     int64_t st_launches = 0, st_searches = 0, st_queries = 0;
     int st_last_kprime = 0, st_last_levels = 0, st_last_path = 0;

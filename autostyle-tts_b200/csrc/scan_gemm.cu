@@ -1,9 +1,373 @@
-// K3 placeholder until the tcgen05 kernel lands in this file.
+// K3: tensor-core scan for large query batches — a dense Q x X^T contraction on tcgen05 with the
+// top-k selection fused into the TMEM epilogue (no [B, N] score matrix ever reaches HBM).
+//
+//   A (M) = 128 queries per CTA (256 per CTA pair), bf16, K-major, TMA -> 128B-swizzled smem
+//   B (N) = 256 database rows per tile (each CTA of a pair loads 128 of them)
+//   D     = fp32 accumulators in TMEM: lane = query, column = database row, 2 x 256 columns
+//           (double buffered: the MMA of tile t+1 overlaps the epilogue of tile t)
+//   roles = warp 0 TMA producer | warp 1 tcgen05.mma issuer (one elected thread, leader CTA)
+//           | warp 2 TMEM allocator | warps 4-7 epilogue
+//   epilogue: thread t owns query lane t.  tcgen05.ld 32 columns -> max tree -> one compare with the
+//           query's running threshold held in a register; only survivors build a 64-bit key and
+//           are appended to the query's candidate buffer (global atomics, rare).
+// Work split: CTA (pair) c visits row groups c, c+C, ... of the level and sweeps ALL query blocks
+// over each group, so a database tile is read from HBM once and re-used from L2.
+// Algorithmic flops per launch: 2 * nq_pad * rows_visited * D_pad.
+#include <cuda.h>
+
 #include "avs_internal.h"
 
-int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
-    (void)s; (void)nq; (void)lv; (void)cap; (void)st;
-    avs_set_error("tensor-core scan is not built into this library");
-    return AVS_E_STATE;
+namespace {
+
+constexpr int BLOCK_M = 128;        // queries per CTA
+constexpr int BLOCK_N = 256;        // database rows per tile (== AVS_GROUP_ROWS)
+constexpr int BLOCK_K = 64;         // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
+
+template <int CG> struct Cfg {
+    static constexpr int LOAD_N = BLOCK_N / CG;                  // X rows loaded by each CTA
+    static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = CG == 1 ? 4 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_local, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t hint) {
+    if constexpr (CG == 1) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                     ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+    } else {
+        // completion is signalled on the LEADER CTA's barrier (peer bit cleared), as CUTLASS SM100_TMA_2SM_LOAD does
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                     ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint) : "memory");
+    }
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+
+// tcgen05.commit: arrive on an mbarrier once every MMA issued so far by this thread has retired.
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;  // the barrier at the same offset in both CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    }
+}
+
+// K-major, 128-byte swizzle: rows are 128 B apart inside an 8-row atom, atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                             // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct PipeState {
+    uint32_t stage = 0, phase = 0;
+    template <int N> __device__ __forceinline__ void advance() {
+        if (++stage == N) { stage = 0; phase ^= 1; }
+    }
+};
+
+template <int CG>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                 int64_t n_rows, int n_qblocks, int num_k_blocks, AvsLevel lv, const u64* __restrict__ tau,
+                 u64* __restrict__ cand, int* __restrict__ cnt, int cap) {
+    using C = Cfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES] TMA bytes landed (leader CTA's copy is the live one)
+    uint64_t* empty_bar = bars + C::STAGES;          // [STAGES] MMA has consumed the stage
+    uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] accumulator ready for the epilogue
+    uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] accumulator drained (leader CTA's copy is live)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(smem_u32(full_bar + i), CG);   // one arrive(+expect_tx) per CTA of the pair
+            mbar_init(smem_u32(empty_bar + i), 1);   // one tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);       // one tcgen05.commit
+            mbar_init(smem_u32(tempty_bar + i), 4 * CG); // one arrive per epilogue warp of every CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            PipeState ps;
+            for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
+                const int64_t g = j * lv.stride;
+                if (lv.skip != 0 && (g % lv.skip) == 0) continue;
+                const int x_row = (int)(g * BLOCK_N + cta_rank * C::LOAD_N);
+                for (int qb = 0; qb < n_qblocks; ++qb) {
+                    const int q_row = (qb * CG + (int)cta_rank) * BLOCK_M;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        mbar_wait(smem_u32(empty_bar + ps.stage), ps.phase ^ 1);
+                        const uint32_t fb = smem_u32(full_bar + ps.stage);
+                        uint8_t* sa = smem + ps.stage * C::STAGE_BYTES;
+                        if (CG == 1 || leader) mbar_arrive_expect_tx(fb, C::STAGE_BYTES * CG);
+                        else mbar_arrive_remote(fb, 0);
+                        tma_load_2d<CG>(&map_q, fb, smem_u32(sa), kb * BLOCK_K, q_row, HINT_EVICT_LAST);
+                        tma_load_2d<CG>(&map_x, fb, smem_u32(sa + A_STAGE_BYTES), kb * BLOCK_K, x_row, HINT_EVICT_NORMAL);
+                        ps.template advance<C::STAGES>();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA, one lane) =====
+        if (leader && lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128 * CG
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                   ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
+            PipeState ps;
+            uint32_t acc = 0, acc_phase = 0;
+            for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
+                const int64_t g = j * lv.stride;
+                if (lv.skip != 0 && (g % lv.skip) == 0) continue;
+                for (int qb = 0; qb < n_qblocks; ++qb) {
+                    mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        mbar_wait(smem_u32(full_bar + ps.stage), ps.phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + ps.stage * C::STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in 16-byte units
+                            umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit<CG>(smem_u32(empty_bar + ps.stage));   // frees the smem stage (both CTAs)
+                        ps.template advance<C::STAGES>();
+                    }
+                    umma_commit<CG>(smem_u32(tfull_bar + acc));            // accumulator complete (both CTAs)
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = query lane =====
+        const int ew = warp & 3;                       // TMEM lane quarter this warp may touch
+        uint32_t acc = 0, acc_phase = 0;
+        for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
+            const int64_t g = j * lv.stride;
+            if (lv.skip != 0 && (g % lv.skip) == 0) continue;
+            const int64_t row0 = g * BLOCK_N;
+            for (int qb = 0; qb < n_qblocks; ++qb) {
+                const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;
+                const u64 tau_k = tau[q];
+                const float tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k);  // NaN for padding slots: never accepts
+                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_base = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(t_base + c0, v);
+                    tmem_ld_wait();
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+                    if (m >= tau_f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float s = __uint_as_float(v[i]);
+                            const int64_t row = row0 + c0 + i;
+                            if (s >= tau_f && row < n_rows) {
+                                const u64 key = avs_make_key(s, (uint32_t)row);
+                                if (key >= tau_k) {
+                                    const int pos = atomicAdd(cnt + q, 1);
+                                    if (pos < cap) cand[(size_t)q * cap + pos] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
+                    else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    if constexpr (CG == 1) __syncthreads(); else cluster_sync_all();
+    if (warp == 2) {
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, dpad] tensor, box = 64 elements (128 B) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int dpad, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { avs_set_error("cuTensorMapEncodeTiled is not available from the driver"); return AVS_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { avs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld, dpad %d)", (int)r, (long long)rows, dpad); return AVS_E_CUDA; }
+    return AVS_OK;
+}
+
+template <int CG>
+int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
+    using C = Cfg<CG>;
+    const int q_block = BLOCK_M * CG;
+    const int nq_pad = (nq + 255) / 256 * 256;            // prep_queries pads to 256: whole blocks for both CG
+    const int n_qblocks = (nq + q_block - 1) / q_block;
+    CUtensorMap mq, mx;
+    AVS_CHECK(make_map(&mq, s->sc.qb, nq_pad, s->dpad, BLOCK_M));
+    AVS_CHECK(make_map(&mx, s->xb, s->capacity, s->dpad, C::LOAD_N));
+    static bool attr = false;
+    if (!attr) {
+        AVS_CUDA(cudaFuncSetAttribute(scan_gemm_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr = true;
+    }
+    int64_t clusters = s->num_sms / CG;
+    if (clusters > lv.n_iter) clusters = lv.n_iter;
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    AVS_CUDA(cudaLaunchKernelEx(&cfg, scan_gemm_kernel<CG>, mq, mx, s->count, n_qblocks, s->dpad / BLOCK_K, lv,
+                                (const u64*)s->sc.tau, s->sc.cand, s->sc.cnt, cap));
+    s->st_launches++;
+    return AVS_OK;
+}
+
+}  // namespace
+
+int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
+    if (s->opt_cta_group == 1) return launch<1>(s, nq, lv, cap, st);
+    return launch<2>(s, nq, lv, cap, st);
+}
+
 void avs_gemm_state_free(avs_store* s) { s->gemm_state = nullptr; }

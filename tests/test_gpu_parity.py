@@ -285,3 +285,45 @@ def test_two_gpu_sharded_search(pkg):
         _check(a_ids.cpu().numpy(), a_d.cpu().numpy(), exp_ids, exp_d)
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("n,d,nq,k,metric", [(1000, 64, 20, 10, "COSINE"), (5000, 768, 64, 10, "COSINE"),
+                                             (2560, 128, 300, 5, "COSINE"), (70000, 256, 130, 10, "COSINE"),
+                                             (20000, 1024, 257, 100, "COSINE"), (4000, 100, 33, 1, "IP"),
+                                             (130, 6144, 130, 5, "COSINE")])
+def test_tensor_core_scan_matches_oracle(pkg, cta_group, n, d, nq, k, metric):
+    """K3 (tcgen05 / TMEM / TMA, fused threshold epilogue), single-CTA and CTA-pair variants."""
+    X, ids, Q = _data(n, d, nq, seed=n + nq, scale=(metric == "COSINE"))
+    st = pkg.Store(d, metric, capacity=n)
+    try:
+        st.insert(X, ids)
+        st.set_option("scan_path", 2)
+        st.set_option("cta_group", cta_group)
+        got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
+        assert st.stat("last_scan_path") == 2
+        exp_ids, exp_d, exp_rows = (fs.search_large if n > 20000 else fs.search)(X, ids, Q, k, metric)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert np.array_equal(got_rows, exp_rows)
+        assert st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
+
+
+def test_auto_path_switches_to_tensor_cores_and_agrees_with_gemv(pkg):
+    n, d, k = 50_000, 768, 10
+    X, ids, Q = _data(n, d, 48, seed=4, scale=False)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        a = st.search(Q, k)
+        assert st.stat("last_scan_path") == 2                  # 48 queries: tensor-core scan
+        st.set_option("scan_path", 1)
+        b = st.search(Q, k)
+        assert st.stat("last_scan_path") == 1
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        st.set_option("scan_path", 0)
+        st.search(Q[:3], k)
+        assert st.stat("last_scan_path") == 1                  # 3 queries: HBM-bound warp-dot scan
+    finally:
+        st.close()
