@@ -17,7 +17,7 @@ typedef unsigned long long u64;
 #define AVS_MAX_KPRIME 256      // largest oversampled candidate list
 #define AVS_REPAIR_CAP 4096     // exact-repair collection buffer per flagged query
 #define AVS_MAX_REPAIR_Q 256    // flagged queries repaired per search
-#define AVS_MAX_LEVELS 6
+#define AVS_MAX_LEVELS 12
 
 // ---- error plumbing -------------------------------------------------------------------------
 void avs_set_error(const char* fmt, ...);
@@ -73,6 +73,9 @@ struct AvsLevel {
     int64_t n_iter;
     int64_t stride;
     int64_t skip;
+    int64_t ratio;    // skip / stride (0 or 1: nothing skipped)
+    int64_t n_visit;  // groups actually visited = n_iter - ceil(n_iter / ratio)
+    int dense;   // 1: threshold-free level - every visited row is stored at slot (j*256 + column), no atomics
 };
 
 struct AvsScratch {
@@ -130,7 +133,7 @@ struct avs_store {
     int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 9, opt_ratio = 32, opt_force_repair = 0,
         opt_cta_group = 2;
     // stats
-    int64_t st_launches = 0, st_searches = 0, st_queries = 0;
+    int64_t st_launches = 0, st_searches = 0, st_queries = 0, st_last_final_rows = 0;
     int st_last_kprime = 0, st_last_levels = 0, st_last_path = 0;
     // scan timing hook
     bool timing = false;

@@ -23,7 +23,9 @@ constexpr int BLOCK_M = 128;        // queries per CTA
 constexpr int BLOCK_N = 256;        // database rows per tile (== AVS_GROUP_ROWS)
 constexpr int BLOCK_K = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int TAU_CACHE = 2048;         // thresholds of every query the CTA sweeps, cached in smem
+constexpr int STASH = 8;                // per-thread survivor stash (keys) between slot reservations
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -33,7 +35,7 @@ template <int CG> struct Cfg {
     static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = CG == 1 ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAU_CACHE * 8 + 256 * STASH * 8;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -45,7 +47,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_local, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -125,7 +127,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// m-th row group a level visits: groups j*stride, j = 0.., leaving out every ratio-th j (seen by a sparser level)
+__device__ __forceinline__ int64_t level_group(const AvsLevel& lv, int64_t m) {
+    const int64_t j = lv.ratio > 1 ? m + m / (lv.ratio - 1) + 1 : m;
+    return j * lv.stride;
+}
 
 struct PipeState {
     uint32_t stage = 0, phase = 0;
@@ -148,11 +168,20 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] accumulator ready for the epilogue
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] accumulator drained (leader CTA's copy is live)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    u64* tau_smem = reinterpret_cast<u64*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    u64* stash_smem = tau_smem + TAU_CACHE;
+    const int n_tau = n_qblocks * BLOCK_M * CG;
+    const bool tau_cached = n_tau <= TAU_CACHE;
+    if (tau_cached)
+        for (int i = threadIdx.x; i < n_tau; i += GEMM_THREADS) tau_smem[i] = tau[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
     const bool leader = cta_rank == 0;
     const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+    // work unit = (visited row group, query block); units are dealt round-robin to the CTAs (pairs), so the
+    // CTAs that run side by side sweep the query blocks over the same database tile: one HBM read, L2 re-use
+    const int64_t n_tiles = lv.n_visit * n_qblocks;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -160,12 +189,12 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
-            mbar_init(smem_u32(full_bar + i), CG);   // one arrive(+expect_tx) per CTA of the pair
+            mbar_init(smem_u32(full_bar + i), 1);    // leader's arrive.expect_tx covers the bytes of both CTAs
             mbar_init(smem_u32(empty_bar + i), 1);   // one tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);       // one tcgen05.commit
-            mbar_init(smem_u32(tempty_bar + i), 4 * CG); // one arrive per epilogue warp of every CTA
+            mbar_init(smem_u32(tempty_bar + i), 8 * CG); // one arrive per epilogue warp of every CTA
         }
         fence_barrier_init();
     }
@@ -187,18 +216,18 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== TMA producer (one lane) =====
         if (lane == 0) {
             PipeState ps;
-            for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
-                const int64_t g = j * lv.stride;
-                if (lv.skip != 0 && (g % lv.skip) == 0) continue;
-                const int x_row = (int)(g * BLOCK_N + cta_rank * C::LOAD_N);
-                for (int qb = 0; qb < n_qblocks; ++qb) {
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                {
+                    const int64_t m = t / n_qblocks;
+                    const int qb = (int)(t - m * n_qblocks);
+                    const int64_t g = level_group(lv, m);
+                    const int x_row = (int)(g * BLOCK_N + cta_rank * C::LOAD_N);
                     const int q_row = (qb * CG + (int)cta_rank) * BLOCK_M;
                     for (int kb = 0; kb < num_k_blocks; ++kb) {
                         mbar_wait(smem_u32(empty_bar + ps.stage), ps.phase ^ 1);
                         const uint32_t fb = smem_u32(full_bar + ps.stage);
                         uint8_t* sa = smem + ps.stage * C::STAGE_BYTES;
                         if (CG == 1 || leader) mbar_arrive_expect_tx(fb, C::STAGE_BYTES * CG);
-                        else mbar_arrive_remote(fb, 0);
                         tma_load_2d<CG>(&map_q, fb, smem_u32(sa), kb * BLOCK_K, q_row, HINT_EVICT_LAST);
                         tma_load_2d<CG>(&map_x, fb, smem_u32(sa + A_STAGE_BYTES), kb * BLOCK_K, x_row, HINT_EVICT_NORMAL);
                         ps.template advance<C::STAGES>();
@@ -214,10 +243,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                    ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
             PipeState ps;
             uint32_t acc = 0, acc_phase = 0;
-            for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
-                const int64_t g = j * lv.stride;
-                if (lv.skip != 0 && (g % lv.skip) == 0) continue;
-                for (int qb = 0; qb < n_qblocks; ++qb) {
+            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                {
                     mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -240,53 +267,116 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = query lane =====
+        // ===== epilogue: 8 warps; thread = (query lane, column half) =====
         const int ew = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int half = (warp - 4) >> 2;              // columns [half*128, half*128 + 128) of the tile
         uint32_t acc = 0, acc_phase = 0;
-        for (int64_t j = cluster_id; j < lv.n_iter; j += n_clusters) {
-            const int64_t g = j * lv.stride;
-            if (lv.skip != 0 && (g % lv.skip) == 0) continue;
-            const int64_t row0 = g * BLOCK_N;
-            for (int qb = 0; qb < n_qblocks; ++qb) {
-                const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;
-                const u64 tau_k = tau[q];
-                const float tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k);  // NaN for padding slots: never accepts
-                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-                tc_fence_after();
-                const uint32_t t_base = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld32(t_base + c0, v);
-                    tmem_ld_wait();
-                    float m = __uint_as_float(v[0]);
+        u64* const my_stash = stash_smem + (size_t)(threadIdx.x - 128) * STASH;
+        // survivors of a tile wait in this thread's shared-memory stash; their slots in the query's candidate
+        // buffer are reserved by ONE atomicAdd issued at the end of the tile and consumed a tile later, so the
+        // L2 round trip of the atomic never stalls the warp
+        u64* pend_dst = nullptr;
+        int pend_n = 0, pend_pos = 0;
+        auto flush_pending = [&]() {
+            for (int i = 0; i < pend_n; ++i)
+                if (pend_pos + i < cap) pend_dst[pend_pos + i] = my_stash[i];
+            pend_n = 0;
+        };
+        for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+            const int64_t m = t / n_qblocks;
+            const int qb = (int)(t - m * n_qblocks);
+            const int64_t row0 = level_group(lv, m) * BLOCK_N + half * 128;
+            const bool has_pad = row0 + 128 > n_rows;  // only the last group of the store can hold padding rows
+            const int valid_cols = has_pad ? (int)(n_rows > row0 ? n_rows - row0 : 0) : 128;
+            const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;
+            const u64 tau_k = tau_cached ? tau_smem[q] : tau[q];
+            const float tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k);  // NaN for padding slots: never accepts
+            u64* const my_cand = cand + (size_t)q * cap;
+            flush_pending();
+            int n_stash = 0;
+            auto reserve = [&]() {
+                pend_n = n_stash;
+                pend_dst = my_cand;
+                pend_pos = atomicAdd(cnt + q, n_stash);   // result is first touched by flush_pending()
+                n_stash = 0;
+            };
+            // 32 scores of this thread's query.  Dense level (threshold-free, the sparsest level): every score goes
+            // to its own slot, no atomics.  Otherwise 4 independent group maxima (short dependency chains) and ONE
+            // compare against the threshold; only a qualifying chunk builds the bit mask of its survivors.
+            auto process = [&](const uint32_t (&v)[32], int col0) {
+                if (lv.dense) {
+                    u64* dst = my_cand + (size_t)m * BLOCK_N + half * 128 + col0;
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-                    if (m >= tau_f) {
+                    for (int i = 0; i < 32; ++i)
+                        dst[i] = (col0 + i < valid_cols && tau_k != ~0ull) ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
+                    return;
+                }
+                float gm[4];
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    const float a = fmaxf(fmaxf(__uint_as_float(v[8 * gi]), __uint_as_float(v[8 * gi + 1])), __uint_as_float(v[8 * gi + 2]));
+                    const float b = fmaxf(fmaxf(__uint_as_float(v[8 * gi + 3]), __uint_as_float(v[8 * gi + 4])), __uint_as_float(v[8 * gi + 5]));
+                    gm[gi] = fmaxf(fmaxf(__uint_as_float(v[8 * gi + 6]), __uint_as_float(v[8 * gi + 7])), fmaxf(a, b));
+                }
+                const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                if (mx >= tau_f) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= tau_f ? 1u : 0u) << i;
+                    if (has_pad) {
+                        const int vc = valid_cols - col0;
+                        mask = vc >= 32 ? mask : (vc <= 0 ? 0u : (mask & ((1u << vc) - 1)));
+                    }
+                    while (mask) {                     // more than STASH survivors (duplicate-heavy data): drain in rounds
+                        uint32_t sub = mask;
+                        if (n_stash + __popc(mask) > STASH) {
+                            if (n_stash) { reserve(); flush_pending(); }
+                            sub = 0;
+                            uint32_t rest = mask;
+                            for (int b = 0; b < STASH && rest; ++b) { sub |= rest & (0u - rest); rest &= rest - 1; }
+                        }
+                        mask &= ~sub;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float s = __uint_as_float(v[i]);
-                            const int64_t row = row0 + c0 + i;
-                            if (s >= tau_f && row < n_rows) {
-                                const u64 key = avs_make_key(s, (uint32_t)row);
-                                if (key >= tau_k) {
-                                    const int pos = atomicAdd(cnt + q, 1);
-                                    if (pos < cap) cand[(size_t)q * cap + pos] = key;
-                                }
+                            if ((sub >> i) & 1) {
+                                my_stash[n_stash] = avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i));
+                                ++n_stash;
                             }
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
-                    else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
-                }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            };
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N + half * 128;
+            uint32_t va[32], vb[32];
+            __syncwarp();
+            tmem_ld32(t_base, va);
+            tmem_ld_wait();
+            tmem_ld32(t_base + 32, vb);                // in flight while the previous chunk is examined
+            process(va, 0);
+            __syncwarp();
+            tmem_ld_wait();
+            tmem_ld32(t_base + 64, va);
+            process(vb, 32);
+            __syncwarp();
+            tmem_ld_wait();
+            tmem_ld32(t_base + 96, vb);
+            process(va, 64);
+            __syncwarp();
+            tmem_ld_wait();
+            // the accumulator has been copied out completely: hand it back to the MMA before the last compare pass
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
+                else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
             }
+            process(vb, 96);
+            if (n_stash) reserve();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        flush_pending();
     }
 
     tc_fence_before();
@@ -343,7 +433,7 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
         attr = true;
     }
     int64_t clusters = s->num_sms / CG;
-    if (clusters > lv.n_iter) clusters = lv.n_iter;
+    if (clusters > lv.n_visit * n_qblocks) clusters = lv.n_visit * n_qblocks;
     if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG));

@@ -118,49 +118,71 @@ __device__ void bitonic_sort_desc(u64* sm, int P) {
     }
 }
 
-__global__ void __launch_bounds__(256) select_level_kernel(u64* __restrict__ cand, int* __restrict__ cnt, int cap,
-                                                            u64* __restrict__ tau, int j_rank, int is_final,
-                                                            int kprime, int64_t n_rows, u64* __restrict__ topkeys,
-                                                            int* __restrict__ topn, float* __restrict__ bound,
-                                                            int* __restrict__ status) {
+struct SelectArgs {
+    u64* cand; int* cnt; int cap; u64* tau; int j_rank; int is_final; int kprime; int64_t n_rows;
+    u64* topkeys; int* topn; float* bound; int* status; int dense_total; int nq;
+};
+
+// Shared tail of both select paths: `at(e)` returns the e-th best key (0 beyond n), `store(e, key)`
+// is only used by the block path.  Runs on one thread.
+__device__ __forceinline__ void select_emit_scalar(const SelectArgs& a, int q, int total, int n, u64 key_j, u64 key_kp) {
+    if (!a.is_final) {
+        int jj = a.j_rank;
+        if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
+        if (n >= jj) a.tau[q] = key_j;
+        a.cnt[q] = n >= jj ? jj : n;
+        if (total > a.cap) a.status[q] |= ST_OVERFLOW;       // rows were lost for good: force the exact repair
+    } else {
+        const int m = n < a.kprime ? n : a.kprime;
+        a.topn[q] = m;
+        float b;
+        int st = 0;
+        if (total > a.cap || (a.status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }   // lost entries
+        else if ((int64_t)n >= a.n_rows) b = -INFINITY;                   // every row is a candidate
+        else if (n > a.kprime) b = avs_key_score(key_kp);                 // rows outside <= K'-th key
+        else b = a.tau[q] == 0ull ? -INFINITY : avs_key_score(a.tau[q]);  // rows outside < threshold
+        a.bound[q] = b;
+        a.status[q] |= st;
+    }
+}
+
+// One CTA per query: block-wide bitonic sort of the collected keys in shared memory.
+__global__ void __launch_bounds__(256) select_level_kernel(SelectArgs a) {
     extern __shared__ u64 sm[];
-    const int q = blockIdx.x;
-    const int total = cnt[q];
-    const int n = total < cap ? total : cap;
+    __shared__ int s_nz;
+    const int lane = threadIdx.x & 31;
+    const int qq = blockIdx.x;
+    int total = a.dense_total > 0 ? a.dense_total : a.cnt[qq];
+    int n = total < a.cap ? total : a.cap;
     int P = 32;
     while (P < n) P <<= 1;
-    u64* c = cand + (size_t)q * cap;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) sm[i] = i < n ? c[i] : 0ull;
+    u64* c = a.cand + (size_t)qq * a.cap;
+    if (threadIdx.x == 0) s_nz = 0;
     __syncthreads();
+    int nz = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const u64 key = i < n ? c[i] : 0ull;
+        sm[i] = key;
+        nz += key != 0ull;
+    }
+    if (a.dense_total > 0) {                 // dense level: padding slots hold key 0 and sort last
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        if (lane == 0 && nz) atomicAdd(&s_nz, nz);
+    }
+    __syncthreads();
+    if (a.dense_total > 0) { n = s_nz; total = n; }
     bitonic_sort_desc(sm, P);
-    if (!is_final) {
-        int jj = j_rank;
-        if (total > cap) {  // overflowed: the kept entries are a 1/phi subsample of the survivors
-            jj = (int)(((long long)j_rank * cap) / total);
-            if (jj < 1) jj = 1;
-        }
+    int jj = a.j_rank;
+    if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
+    if (!a.is_final) {
         const int keep = n >= jj ? jj : n;
         for (int i = threadIdx.x; i < keep; i += blockDim.x) c[i] = sm[i];
-        if (threadIdx.x == 0) {
-            if (n >= jj) tau[q] = sm[jj - 1];
-            cnt[q] = keep;
-            if (total > cap) status[q] |= ST_OVERFLOW;  // rows were lost for good: force the exact repair
-        }
     } else {
-        const int m = n < kprime ? n : kprime;
-        for (int i = threadIdx.x; i < kprime; i += blockDim.x) topkeys[(size_t)q * kprime + i] = i < m ? sm[i] : 0ull;
-        if (threadIdx.x == 0) {
-            topn[q] = m;
-            float b;
-            int st = 0;
-            if (total > cap || (status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }  // lost entries
-            else if ((int64_t)n >= n_rows) b = -INFINITY;                // every row is a candidate
-            else if (n > kprime) b = avs_key_score(sm[kprime - 1]);      // rows outside <= K'-th key
-            else b = tau[q] == 0ull ? -INFINITY : avs_key_score(tau[q]); // rows outside < threshold
-            bound[q] = b;
-            status[q] |= st;
-        }
+        const int m = n < a.kprime ? n : a.kprime;
+        for (int i = threadIdx.x; i < a.kprime; i += blockDim.x) a.topkeys[(size_t)qq * a.kprime + i] = i < m ? sm[i] : 0ull;
     }
+    if (threadIdx.x == 0) select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -511,27 +533,48 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         return AVS_OK;
     }
 
-    // sampling levels: the sparsest level must fit the collection buffer with threshold 0
+    const bool use_gemm = (s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch);
+    // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th
+    // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
+    // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
+    // last threshold is taken from a quarter of the database); the gemv path keeps fewer, coarser levels.
     const int64_t G = (s->count + AVS_GROUP_ROWS - 1) / AVS_GROUP_ROWS;
     const int64_t rho = s->opt_ratio < 2 ? 2 : s->opt_ratio;
+    int64_t strides[AVS_MAX_LEVELS];
     int L = 1;
-    int64_t stride0 = 1;
-    while (((G + stride0 - 1) / stride0) * AVS_GROUP_ROWS > cap && L < AVS_MAX_LEVELS) { stride0 *= rho; ++L; }
-    AvsLevel lv[AVS_MAX_LEVELS];
-    {
-        int64_t stride = stride0, prev = 0;
-        for (int i = 0; i < L; ++i) {
-            lv[i].stride = stride;
-            lv[i].n_iter = (G + stride - 1) / stride;
-            lv[i].skip = prev;
-            prev = stride;
-            stride /= rho;
-        }
+    strides[0] = 1;
+    while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > cap && L < AVS_MAX_LEVELS) {
+        // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
+        // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
+        const int64_t r = (use_gemm && L <= 3) ? 4 : rho;
+        strides[L] = strides[L - 1] * r;
+        ++L;
     }
-    int j_rank = (int)((16ll * kprime) / rho);
-    if (j_rank < 8) j_rank = 8;
+    AvsLevel lv[AVS_MAX_LEVELS];
+    int j_ranks[AVS_MAX_LEVELS];
+    for (int i = 0; i < L; ++i) {            // level 0 = sparsest
+        const int64_t stride = strides[L - 1 - i];
+        lv[i].stride = stride;
+        lv[i].n_iter = (G + stride - 1) / stride;
+        lv[i].skip = i == 0 ? 0 : strides[L - i];
+        lv[i].ratio = i == 0 ? 0 : lv[i].skip / stride;
+        lv[i].n_visit = lv[i].ratio > 1 ? lv[i].n_iter - (lv[i].n_iter + lv[i].ratio - 1) / lv[i].ratio : lv[i].n_iter;
+        lv[i].dense = (i == 0 && use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ? 1 : 0;
+        // rank whose key becomes the next threshold: expected survivors at the next level = j * ratio
+        int64_t j = 0;
+        if (i < L - 1) {
+            const int64_t ratio = stride / strides[L - 2 - i];
+            // expected survivors by the end of the next level
+            int64_t target;
+            if (use_gemm) target = ratio > 4 ? 8ll * kprime : ((i + 1 == L - 1) ? 4ll * kprime : 2ll * kprime);
+            else target = (i + 1 == L - 1) ? 8ll * kprime : 8ll * kprime;
+            j = target / ratio;
+            if (j < 8) j = 8;
+        }
+        j_ranks[i] = (int)j;
+    }
 
-    const bool use_gemm = (s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch);
+    s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;
     s->st_last_kprime = kprime;
     s->st_last_levels = L;
     s->st_last_path = use_gemm ? 2 : 1;
@@ -560,8 +603,9 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
         }
         if (timed) timing_end(s, st, slot);
-        select_level_kernel<<<nq, 256, (size_t)cap * 8, st>>>(c.cand, c.cnt, cap, c.tau, j_rank, final_level ? 1 : 0,
-                                                               kprime, s->count, c.topkeys, c.topn, bound, c.status);
+        SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, s->count, c.topkeys, c.topn,
+                         bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq};
+        select_level_kernel<<<nq, 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
     }
@@ -644,6 +688,7 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "queries") *out = s->st_queries;
     else if (k == "last_kprime") *out = s->st_last_kprime;
     else if (k == "last_levels") *out = s->st_last_levels;
+    else if (k == "last_final_rows") *out = s->st_last_final_rows;
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k == "repaired_queries" || k == "uncertified_queries") {
         AVS_CUDA(cudaSetDevice(s->device));

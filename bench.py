@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--metric", default="COSINE")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-path", type=int, default=0, help="0 auto, 1 gemv, 2 gemm")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--only-batch", action="store_true", help="skip the extra batch-1 measurement")
     return ap.parse_args()
 
 
@@ -183,6 +185,9 @@ def run_ours(a):
     st = ss.store
     ss.fill_synthetic(SEED_DB)
     st.set_option("scan_path", a.scan_path)
+    for kv in a.opt:
+        key, val = kv.split("=")
+        st.set_option(key, int(val))
     torch.cuda.synchronize()
     rows_local = len(st)
     dpad = (a.dim + 63) // 64 * 64
@@ -221,7 +226,7 @@ def run_ours(a):
         clocks.start()
     windows = []
     results = {}
-    for batch in sorted({a.batch, 1}, reverse=True):
+    for batch in sorted({a.batch} if a.only_batch else {a.batch, 1}, reverse=True):
         q = q_dev[:batch]
         qh = q_pinned[:batch].numpy()
         fn_dev = (lambda: ss.search(q, a.k))
@@ -233,10 +238,7 @@ def run_ours(a):
         scan_ms, scan_n = st.scan_timing(0)
         windows.append(win)
         path, levels = st.stat("last_scan_path"), st.stat("last_levels")
-        # rows the final level visits = all groups minus those sampled by the sparser levels
-        groups = (rows_local + 255) // 256
-        sampled = (groups + 31) // 32 if levels > 1 else 0
-        rows_final = min(rows_local, (groups - sampled) * 256)
+        rows_final = st.stat("last_final_rows")     # rows the final (dense) level visits
         if path == 2:
             work = 2.0 * batch * rows_final * dpad
             roof = {"bound": "tensor", "achieved": work / (scan_ms * 1e-3) / 1e12 if scan_ms else None, "peak": tc_peak,
