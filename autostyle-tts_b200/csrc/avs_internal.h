@@ -78,6 +78,12 @@ struct AvsLevel {
     int dense;   // 1: threshold-free level - every visited row is stored at slot (j*256 + column), no atomics
 };
 
+// m-th row group a level visits: groups j*stride, j = 0.., leaving out every ratio-th j (seen by a sparser level)
+__host__ __device__ __forceinline__ int64_t avs_level_group(const AvsLevel& lv, int64_t m) {
+    const int64_t j = lv.ratio > 1 ? m + m / (lv.ratio - 1) + 1 : m;
+    return j * lv.stride;
+}
+
 struct AvsScratch {
     // query preparation
     float* qf = nullptr;          // [nq_pad, dpad] fp32, normalised for COSINE, zero padded
@@ -130,7 +136,7 @@ struct avs_store {
     AvsScratch sc;
     int num_sms = 148;
     // options
-    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 9, opt_ratio = 32, opt_force_repair = 0,
+    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 4, opt_ratio = 32, opt_force_repair = 0,
         opt_cta_group = 2;
     // stats
     int64_t st_launches = 0, st_searches = 0, st_queries = 0, st_last_final_rows = 0;

@@ -141,12 +141,6 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// m-th row group a level visits: groups j*stride, j = 0.., leaving out every ratio-th j (seen by a sparser level)
-__device__ __forceinline__ int64_t level_group(const AvsLevel& lv, int64_t m) {
-    const int64_t j = lv.ratio > 1 ? m + m / (lv.ratio - 1) + 1 : m;
-    return j * lv.stride;
-}
-
 struct PipeState {
     uint32_t stage = 0, phase = 0;
     template <int N> __device__ __forceinline__ void advance() {
@@ -220,7 +214,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 {
                     const int64_t m = t / n_qblocks;
                     const int qb = (int)(t - m * n_qblocks);
-                    const int64_t g = level_group(lv, m);
+                    const int64_t g = avs_level_group(lv, m);
                     const int x_row = (int)(g * BLOCK_N + cta_rank * C::LOAD_N);
                     const int q_row = (qb * CG + (int)cta_rank) * BLOCK_M;
                     for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -285,7 +279,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
             const int64_t m = t / n_qblocks;
             const int qb = (int)(t - m * n_qblocks);
-            const int64_t row0 = level_group(lv, m) * BLOCK_N + half * 128;
+            const int64_t row0 = avs_level_group(lv, m) * BLOCK_N + half * 128;
             const bool has_pad = row0 + 128 > n_rows;  // only the last group of the store can hold padding rows
             const int valid_cols = has_pad ? (int)(n_rows > row0 ? n_rows - row0 : 0) : 128;
             const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;

@@ -82,13 +82,17 @@ scan_gemv_kernel(const uint4* __restrict__ xb, int packets_per_row, int64_t n_ro
     }
     __syncthreads();
 
-    for (int64_t j = blockIdx.x; j < lv.n_iter; j += gridDim.x) {
-        const int64_t g = j * lv.stride;
-        if (lv.skip != 0 && (g % lv.skip) == 0) continue;
-        const int64_t wrow0 = g * AVS_GROUP_ROWS + warp * 32;
-        for (int rr = 0; rr < 32; rr += GEMV_ROWS) {
-            const int64_t rbase = wrow0 + rr;
-            if (rbase >= n_rows) break;
+    // work unit = 4 consecutive rows; units of the visited groups are dealt round-robin to all warps of the
+    // grid, so neighbouring warps stream neighbouring 4-row packets and even the sparsest level fills the chip
+    constexpr int UNITS = AVS_GROUP_ROWS / GEMV_ROWS;
+    const int64_t n_units = lv.n_visit * UNITS;
+    const int64_t gwarp = (int64_t)blockIdx.x * (GEMV_THREADS / 32) + warp;
+    const int64_t n_gwarps = (int64_t)gridDim.x * (GEMV_THREADS / 32);
+    for (int64_t u = gwarp; u < n_units; u += n_gwarps) {
+        {
+            const int64_t m = u / UNITS;
+            const int64_t rbase = avs_level_group(lv, m) * AVS_GROUP_ROWS + (u - m * UNITS) * GEMV_ROWS;
+            if (rbase >= n_rows) continue;
             float acc[GEMV_ROWS * NQ];
 #pragma unroll
             for (int i = 0; i < GEMV_ROWS * NQ; ++i) acc[i] = 0.f;
@@ -134,7 +138,8 @@ static int launch_gemv(avs_store* s, int q0, const AvsLevel& lv, int cap, cudaSt
         attr_set = true;
     }
     if (smem > 200 * 1024) { avs_set_error("gemv scan: %d queries x %d dims do not fit shared memory", NQ, s->dpad); return AVS_E_INVALID; }
-    int64_t grid = lv.n_iter < (int64_t)s->num_sms * 2 ? lv.n_iter : (int64_t)s->num_sms * 2;
+    const int64_t want = (lv.n_visit * (AVS_GROUP_ROWS / GEMV_ROWS) + GEMV_THREADS / 32 - 1) / (GEMV_THREADS / 32);
+    int64_t grid = want < (int64_t)s->num_sms * 2 ? want : (int64_t)s->num_sms * 2;
     if (grid < 1) grid = 1;
     scan_gemv_kernel<NQ><<<(unsigned)grid, GEMV_THREADS, smem, st>>>(
         reinterpret_cast<const uint4*>(s->xb), ppr, s->count, s->sc.qf + (size_t)q0 * s->dpad, s->dpad,

@@ -147,7 +147,7 @@ __device__ __forceinline__ void select_emit_scalar(const SelectArgs& a, int q, i
 }
 
 // One CTA per query: block-wide bitonic sort of the collected keys in shared memory.
-__global__ void __launch_bounds__(256) select_level_kernel(SelectArgs a) {
+__global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     extern __shared__ u64 sm[];
     __shared__ int s_nz;
     const int lane = threadIdx.x & 31;
@@ -211,24 +211,6 @@ __device__ __forceinline__ double exact_score(const float* __restrict__ x, const
     return dot;
 }
 
-__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ master, const int64_t* __restrict__ ids,
-                                                      const float* __restrict__ q, const double* __restrict__ qnorm,
-                                                      const u64* __restrict__ topkeys, const int* __restrict__ topn,
-                                                      int nq, int kprime, int dim, int metric,
-                                                      double* __restrict__ s64, int64_t* __restrict__ cid) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= (int64_t)nq * kprime) return;
-    const int qi = (int)(w / kprime), c = (int)(w - (int64_t)qi * kprime);
-    if (c >= topn[qi]) {
-        if (lane == 0) { s64[w] = -INFINITY; cid[w] = -1; }
-        return;
-    }
-    const uint32_t row = avs_key_row(topkeys[w]);
-    const double s = exact_score(master + (size_t)row * dim, q + (size_t)qi * dim, dim, qnorm[qi], metric, lane);
-    if (lane == 0) { s64[w] = s; cid[w] = ids[row]; }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Finalize: one CTA per query sorts the <= 256 rescored candidates by (score desc, id asc, row asc)
 // and checks the exactness certificate: every row outside the candidate list has scan score
@@ -242,7 +224,9 @@ __device__ __forceinline__ bool hit_better(const Hit& a, const Hit& b) {
     return a.row < b.row;
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ s64, const int64_t* __restrict__ cid,
+__global__ void __launch_bounds__(1024) finalize_kernel(const float* __restrict__ master, const int64_t* __restrict__ ids,
+                                                       const float* __restrict__ qraw, const double* __restrict__ qnorm,
+                                                       int dim, int metric,
                                                        const u64* __restrict__ topkeys, const int* __restrict__ topn,
                                                        const float* __restrict__ bound, const float* __restrict__ eps,
                                                        int kprime, int k, int64_t n_rows, int force_repair,
@@ -254,11 +238,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     __shared__ Hit sm[AVS_MAX_KPRIME];
     const int q = blockIdx.x, t = threadIdx.x;
     const int n = topn[q];
-    if (t < kprime) {
-        Hit h;
-        if (t < n) { h.s = s64[(size_t)q * kprime + t]; h.id = cid[(size_t)q * kprime + t]; h.row = avs_key_row(topkeys[(size_t)q * kprime + t]); }
-        else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
-        sm[t] = h;
+    {   // K5: exact float64 rescoring, one warp per candidate (8 warps take the K' candidates in turns)
+        const int lane = t & 31, warp = t >> 5;
+        const double qn = qnorm[q];
+        const float* qp = qraw + (size_t)q * dim;
+        for (int c = warp; c < kprime; c += (int)(blockDim.x >> 5)) {
+            Hit h;
+            if (c < n) {
+                h.row = avs_key_row(topkeys[(size_t)q * kprime + c]);
+                h.s = exact_score(master + (size_t)h.row * dim, qp, dim, qn, metric, lane);
+                h.id = ids[h.row];
+            } else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
+            if (lane == 0) sm[c] = h;
+        }
     }
     __syncthreads();
     for (int k2 = 2; k2 <= kprime; k2 <<= 1) {
@@ -538,6 +530,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
     // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
     // last threshold is taken from a quarter of the database); the gemv path keeps fewer, coarser levels.
+    const bool fine_levels = use_gemm && nq >= 192;   // compute-bound regime only: extra levels cost launches
     const int64_t G = (s->count + AVS_GROUP_ROWS - 1) / AVS_GROUP_ROWS;
     const int64_t rho = s->opt_ratio < 2 ? 2 : s->opt_ratio;
     int64_t strides[AVS_MAX_LEVELS];
@@ -546,7 +539,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > cap && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
-        const int64_t r = (use_gemm && L <= 3) ? 4 : rho;
+        const int64_t r = (fine_levels && L <= 3) ? 4 : rho;
         strides[L] = strides[L - 1] * r;
         ++L;
     }
@@ -566,7 +559,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             const int64_t ratio = stride / strides[L - 2 - i];
             // expected survivors by the end of the next level
             int64_t target;
-            if (use_gemm) target = ratio > 4 ? 8ll * kprime : ((i + 1 == L - 1) ? 4ll * kprime : 2ll * kprime);
+            if (fine_levels) target = ratio > 4 ? 8ll * kprime : ((i + 1 == L - 1) ? 4ll * kprime : 2ll * kprime);
             else target = (i + 1 == L - 1) ? 8ll * kprime : 8ll * kprime;
             j = target / ratio;
             if (j < 8) j = 8;
@@ -580,7 +573,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     s->st_last_path = use_gemm ? 2 : 1;
 
     AVS_CUDA(cudaMemsetAsync(c.flagged, 0, sizeof(int), st));
-    prep_queries_kernel<<<nq_pad, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
+    const int n_slots = use_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
+    prep_queries_kernel<<<n_slots, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
                                                 c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
@@ -605,19 +599,12 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         if (timed) timing_end(s, st, slot);
         SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, s->count, c.topkeys, c.topn,
                          bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq};
-        select_level_kernel<<<nq, 256, (size_t)cap * 8, st>>>(sa);
+        select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
     }
 
-    {
-        const int64_t warps = (int64_t)nq * kprime;
-        rescore_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(s->master, s->ids, q, c.qnorm, c.topkeys, c.topn, nq,
-                                                                    kprime, s->dim, s->metric, c.s64, c.cid);
-        s->st_launches++;
-        AVS_CUDA(cudaGetLastError());
-    }
-    finalize_kernel<<<nq, 256, 0, st>>>(c.s64, c.cid, c.topkeys, c.topn, bound, use_gemm ? c.eps_gemm : c.eps_gemv, kprime, k,
+    finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, use_gemm ? c.eps_gemm : c.eps_gemv, kprime, k,
                                         s->count, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
                                         c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
     s->st_launches++;

@@ -239,13 +239,17 @@ def run_ours(a):
         windows.append(win)
         path, levels = st.stat("last_scan_path"), st.stat("last_levels")
         rows_final = st.stat("last_final_rows")     # rows the final (dense) level visits
-        if path == 2:
-            work = 2.0 * batch * rows_final * dpad
+        flops = 2.0 * batch * rows_final * dpad
+        passes = (batch + 7) // 8 if path == 1 else 1
+        nbytes = float(passes) * rows_final * dpad * 2
+        # the tensor-core scan is HBM-bound for small batches: report against whichever roof binds
+        tensor_bound = path == 2 and flops / (tc_peak * 1e12) > nbytes / (hbm_peak * 1e9)
+        if tensor_bound:
+            work = flops
             roof = {"bound": "tensor", "achieved": work / (scan_ms * 1e-3) / 1e12 if scan_ms else None, "peak": tc_peak,
                     "unit": "TFLOP/s"}
         else:
-            passes = (batch + 7) // 8
-            work = float(passes) * rows_final * dpad * 2
+            work = nbytes
             roof = {"bound": "hbm", "achieved": work / (scan_ms * 1e-3) / 1e9 if scan_ms else None, "peak": hbm_peak,
                     "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
