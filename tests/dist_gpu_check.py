@@ -1,0 +1,56 @@
+"""Multi-GPU parity check for the row-sharded search (run under torchrun on the GPU box; one
+process per GPU, NCCL).  Not collected by pytest: the `-m gpu` suite runs on one GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_gpu_check.py
+
+Every rank fills its contiguous shard of the synthetic stream on device, all ranks search the same
+query batch (local exact top-k -> one ncclAllGather -> merge), and the merged result must equal the
+oracle's answer on the whole database, on every rank, for both scan paths.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import flat_search as fs  # noqa: E402
+
+sharded = importlib.import_module("autostyle-tts_b200.sharded")
+synth = importlib.import_module("autostyle-tts_b200.synth")
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for (n, d, nq, k, metric) in [(200_003, 256, 5, 10, "COSINE"), (150_000, 768, 96, 10, "COSINE"),
+                                  (64_000, 128, 300, 100, "IP"), (1000, 64, 3, 50, "COSINE")]:
+        ss = sharded.ShardedStore(d, metric, n, rank, world, device=local)
+        ss.fill_synthetic(42)
+        Q = synth.planted_queries(43, 42, n, nq, d)
+        ids, sc = ss.search(torch.from_numpy(Q).cuda(), k)
+        ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+        X = np.concatenate([synth.synth_rows(42, lo, min(50_000, n - lo), d) for lo in range(0, n, 50_000)])
+        exp_ids, exp_d, _ = fs.search_large(X, np.arange(n), Q, k, metric)
+        good = np.array_equal(ids, exp_ids) and np.all(np.abs(sc - exp_d) <= 1e-5 * np.maximum(1, np.abs(exp_d)))
+        flag = torch.tensor([1 if good else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"world={world} n={n} d={d} nq={nq} k={k} {metric}: {'OK' if flag.item() else 'MISMATCH'} "
+                  f"(shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
+                  f"uncertified {ss.store.stat('uncertified_queries')})", flush=True)
+        ok &= bool(flag.item())
+        ss.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

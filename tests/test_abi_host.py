@@ -144,3 +144,36 @@ def test_shard_range_matches_oracle():
         assert [sh.shard_range(n, r, w) for r in range(w)] == fs.shard_bounds(n, w)
     with pytest.raises(ValueError):
         sh.shard_range(10, 4, 4)
+
+
+REF_DB = "/root/reference/milvus/milvus_demo.db"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DB), reason="reference tree only exists in the authoring container")
+def test_product_reader_opens_the_reference_shipped_db(f1):
+    """the drop-in opens the file the reference's scripts share, unchanged."""
+    mldb = load_pkg("milvus_lite_db")
+    import shutil, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "milvus_demo.db")
+        shutil.copy(REF_DB, path)                       # the reference tree is read-only; sqlite wants a writable dir
+        f = mldb.MilvusLiteFile(path)
+        assert sorted(f.list_collections()) == ["demo_collection", "embeddings_biographies_collection"]
+        schema, index = f.read_meta("embeddings_biographies_collection")
+        assert [x["name"] for x in schema["fields"]] == ["id", "vector", "$meta"]
+        assert schema["fields"][1]["dim"] == 6144 and schema["enable_dynamic_field"]
+        assert index["metric_type"] == "COSINE" and index["index_type"] == "AUTOINDEX"
+        rows = f.load_rows("embeddings_biographies_collection")
+        assert len(rows) == 130
+        assert np.array_equal(np.stack([r["vector"] for r in rows]), f1["X"])
+        assert [r["id"] for r in rows] == f1["pks"].tolist()
+        assert [r["$meta"] for r in rows] == f1["meta"]
+        assert f.load_rows("demo_collection") == []
+        f.close()
+        # and the client catalogue (no GPU needed until the first search)
+        pkg = load_pkg()
+        c = pkg.MilvusClient(path)
+        assert c.has_collection("embeddings_biographies_collection")
+        assert c.get_collection_stats("embeddings_biographies_collection")["row_count"] == 130
+        assert c.describe_collection("embeddings_biographies_collection")["metric_type"] == "COSINE"
+        c.close()

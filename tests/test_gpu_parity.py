@@ -327,3 +327,29 @@ def test_auto_path_switches_to_tensor_cores_and_agrees_with_gemv(pkg):
         assert st.stat("last_scan_path") == 1                  # 3 queries: HBM-bound warp-dot scan
     finally:
         st.close()
+
+
+def test_search_json_front_end_emits_the_tts_contract(pkg, f1, tmp_path):
+    """JSONL of precomputed embeddings -> the JSONL tts_with_rag.py:77-96 reads."""
+    sj = load_pkg("search_json")
+    X, pks, meta, kat = f1["X"], f1["pks"], f1["meta"], f1["kat"]
+    db = str(tmp_path / "milvus_demo.db")
+    c = pkg.MilvusClient(db)
+    c.create_collection(collection_name=sj.DEFAULT_COLLECTION, dimension=6144)
+    c.insert(sj.DEFAULT_COLLECTION, [{"id": int(pks[i]), "file_id": meta[i]["file_id"], "vector": X[i], "text": meta[i]["text"]}
+                                    for i in range(130)])
+    c.close()
+    lines = [{"zh_text": f"line {i}", "speaker": "spk", "whisper": "w", "embedding": kat["pert_queries"][i].tolist()}
+             for i in range(6)]
+    lines.append({"zh_text": "broken", "speaker": "spk", "embedding": [1.0, 2.0]})       # wrong dimension -> N/A row
+    src, dst = tmp_path / "in.jsonl", tmp_path / "search_results.json"
+    src.write_text("\n".join(json.dumps(l) for l in lines), encoding="utf-8")
+    sj.main(["--input_json", str(src), "--output_json", str(dst), "--db_path", db, "--prefix", "/styles/"])
+    out = [json.loads(l) for l in dst.read_text(encoding="utf-8").splitlines()]
+    assert len(out) == 7
+    for i in range(6):
+        row = int(kat["pert_rows"][i, 0])
+        assert set(out[i]) == {"zh_text", "speaker", "whisper", "retrieved_file_id", "retrieved_text", "distance"}
+        assert out[i]["retrieved_file_id"] == "/styles/" + meta[row]["file_id"] and out[i]["retrieved_text"] == meta[row]["text"]
+        assert abs(out[i]["distance"] - float(kat["pert_dist"][i, 0])) <= RTOL
+    assert out[6]["retrieved_file_id"] == "N/A" and out[6]["distance"] is None
