@@ -314,9 +314,16 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
                 if (mx >= tau_f) {
-                    uint32_t mask = 0;
+                    uint32_t mask = 0;                 // survivors, looked for only inside the groups that qualify
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= tau_f ? 1u : 0u) << i;
+                    for (int gi = 0; gi < 4; ++gi) {
+                        if (gm[gi] >= tau_f) {
+                            uint32_t mg = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) mg |= (__uint_as_float(v[8 * gi + i]) >= tau_f ? 1u : 0u) << i;
+                            mask |= mg << (8 * gi);
+                        }
+                    }
                     if (has_pad) {
                         const int vc = valid_cols - col0;
                         mask = vc >= 32 ? mask : (vc <= 0 ? 0u : (mask & ((1u << vc) - 1)));
@@ -331,10 +338,15 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         }
                         mask &= ~sub;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if ((sub >> i) & 1) {
-                                my_stash[n_stash] = avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i));
-                                ++n_stash;
+                        for (int gi = 0; gi < 4; ++gi) {
+                            if ((sub >> (8 * gi)) & 0xFFu) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if ((sub >> (8 * gi + i)) & 1) {
+                                        my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), (uint32_t)(row0 + col0 + 8 * gi + i));
+                                        ++n_stash;
+                                    }
+                                }
                             }
                         }
                     }

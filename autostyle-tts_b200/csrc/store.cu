@@ -97,6 +97,64 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __rest
     }
 }
 
+// Single-pass variant for dim % 4 == 0 and dim <= 128 * MAXV: the row stays in registers between the norm and
+// the rounding pass, so every fp32 element is read from HBM exactly once (4 B in, 2 B out per element).
+template <int MAXV>
+__global__ void __launch_bounds__(256) normalize_rows_reg_kernel(const float* __restrict__ master,
+                                                                 __nv_bfloat16* __restrict__ xb,
+                                                                 float* __restrict__ inv_norm,
+                                                                 float* __restrict__ gstat, int64_t row0,
+                                                                 int64_t n, int dim, int dpad, int metric) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim >> 2, nvec_pad = dpad >> 2;
+    float local_r = 0.f, local_n = 0.f;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t row = row0 + r;
+        const float4* x4 = reinterpret_cast<const float4*>(master + row * dim);
+        float4 buf[MAXV];
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = lane + 32 * i;
+            buf[i] = c < nvec ? __ldcs(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += (double)buf[i].x * buf[i].x + (double)buf[i].y * buf[i].y + (double)buf[i].z * buf[i].z + (double)buf[i].w * buf[i].w;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float nrm = (float)sqrt(ss);
+        const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.f;
+        const float scale = (metric == AVS_METRIC_COSINE) ? inv : 1.0f;
+        float res = 0.f;
+        uint2* o = reinterpret_cast<uint2*>(xb + row * dpad);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec_pad) {
+                const float v0 = buf[i].x * scale, v1 = buf[i].y * scale, v2 = buf[i].z * scale, v3 = buf[i].w * scale;
+                const __nv_bfloat16 b0 = __float2bfloat16_rn(v0), b1 = __float2bfloat16_rn(v1), b2 = __float2bfloat16_rn(v2), b3 = __float2bfloat16_rn(v3);
+                const float d0 = __bfloat162float(b0) - v0, d1 = __bfloat162float(b1) - v1, d2 = __bfloat162float(b2) - v2, d3 = __bfloat162float(b3) - v3;
+                res += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                uint2 pk;
+                pk.x = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                pk.y = (uint32_t)__bfloat16_as_ushort(b2) | ((uint32_t)__bfloat16_as_ushort(b3) << 16);
+                o[c] = pk;
+            }
+        }
+        res = warp_sum(res);
+        if (lane == 0) {
+            inv_norm[row] = inv;
+            local_r = fmaxf(local_r, sqrtf(res));
+            local_n = fmaxf(local_n, nrm);
+        }
+    }
+    if (lane == 0) {
+        if (local_r > 0.f) atomic_max_nonneg(gstat + 0, local_r);
+        if (local_n > 0.f) atomic_max_nonneg(gstat + 1, local_n);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Synthetic rows (benchmark utility).  Element (row, col) of stream `seed`:
 //   z = mix(mix(seed + row*G1) ^ (col+1)*G2)         (splitmix64 finaliser)
@@ -247,8 +305,16 @@ static int launch_normalize(avs_store* s, int64_t row0, int64_t n, cudaStream_t 
     int64_t blocks = (n + 7) / 8;
     int64_t maxb = (int64_t)s->num_sms * 8;
     if (blocks > maxb) blocks = maxb;
-    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->master, s->xb, s->inv_norm, s->gstat, row0, n,
-                                                            s->dim, s->dpad, s->metric);
+    const bool reg_path = (s->dim % 4 == 0) && (s->dpad / 4 <= 32 * 16);   // master rows are 16-byte aligned then
+    if (reg_path && s->dpad / 4 <= 32 * 8)
+        normalize_rows_reg_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(s->master, s->xb, s->inv_norm, s->gstat, row0, n,
+                                                                       s->dim, s->dpad, s->metric);
+    else if (reg_path)
+        normalize_rows_reg_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(s->master, s->xb, s->inv_norm, s->gstat, row0, n,
+                                                                        s->dim, s->dpad, s->metric);
+    else
+        normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->master, s->xb, s->inv_norm, s->gstat, row0, n,
+                                                                s->dim, s->dpad, s->metric);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     return AVS_OK;

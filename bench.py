@@ -134,8 +134,13 @@ def run_reference(a):
     if rank != 0:
         return
     synth = importlib.import_module("autostyle-tts_b200.synth")
+    try:                                               # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     X = host_rows(a, 0, a.rows)                        # unit-norm rows: the cached FLAT/cosine index content
-    nq = min(a.batch, 64)                              # bounded sample of the batch per step
+    nq = min(a.batch, 128)                             # bounded sample of the batch per step
     Q = synth.planted_queries(SEED_Q, SEED_DB, a.rows, a.batch, a.dim)[:nq]
     steps, warm = max(1, min(a.steps, 10)), max(1, min(a.warmup, 2))
     from oracle import flat_search as fs
@@ -154,6 +159,22 @@ def run_reference(a):
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def ncu_traffic(a, batch, path):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/rNN/traffic.json); only valid for the exact workload that capture ran."""
+    import glob
+    if (a.rows, a.dim, a.k) != (1_000_000, 768, 10):
+        return None
+    key = "scan_gemm" if (path == 2 and batch == 1024) else "scan_gemv" if (path == 1 and batch == 1) else None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")))
+    if not key or not files:
+        return None
+    try:
+        return json.load(open(files[-1]))[key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -253,7 +274,7 @@ def run_ours(a):
             roof = {"bound": "hbm", "achieved": work / (scan_ms * 1e-3) / 1e9 if scan_ms else None, "peak": hbm_peak,
                     "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
-        roof.update({"traffic": None, "peak_source": peak_src, "kernel": "scan_gemm (tcgen05)" if path == 2 else "scan_gemv",
+        roof.update({"traffic": ncu_traffic(a, batch, path), "peak_source": peak_src, "kernel": "scan_gemm (tcgen05)" if path == 2 else "scan_gemv",
                      "kernel_ms": scan_ms, "timed_launch_groups": scan_n, "algorithmic_work_per_launch_group": work})
         # end to end through the C-ABI host call (single GPU): pinned host queries in, host hits out
         e2e = None

@@ -224,19 +224,37 @@ def shard_bounds(n: int, world: int):
     return [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
 
 
-def cpu_flat_baseline(Xn: np.ndarray, Q: np.ndarray, k: int, chunk: int = 1 << 18):
-    """The same-box CPU baseline: fp32 BLAS `Q @ Xn.T` on
-    pre-normalised rows + argpartition + sort of the survivors.  Returns
-    (rows[nq,k], scores fp32[nq,k])."""
-    nq = Q.shape[0]
-    best_s = np.empty((nq, 0), dtype=np.float32)
-    best_r = np.empty((nq, 0), dtype=np.int64)
-    for lo in range(0, Xn.shape[0], chunk):
+def cpu_flat_baseline(Xn: np.ndarray, Q: np.ndarray, k: int, chunk: int = 1 << 15):
+    """The same-box CPU baseline: fp32 BLAS `Q @ Xn.T` on pre-normalised rows,
+    chunked over N so a score tile stays cache-resident, with a running k-th-best threshold per query
+    (what a FLAT engine's per-query heap amounts to): only scores above the threshold are gathered and
+    merged.  Returns (rows[nq,k], scores fp32[nq,k]) ordered by (score desc, row asc)."""
+    nq, n = Q.shape[0], Xn.shape[0]
+    kk = min(k, n)
+    best_s = np.full((nq, kk), -np.inf, dtype=np.float32)
+    best_r = np.full((nq, kk), -1, dtype=np.int64)
+    thr = np.full(nq, -np.inf, dtype=np.float32)
+    for lo in range(0, n, chunk):
         S = Q @ Xn[lo:lo + chunk].T
-        kk = min(k, S.shape[1])
-        part = np.argpartition(-S, kk - 1, axis=1)[:, :kk]
-        best_s = np.concatenate([best_s, np.take_along_axis(S, part, axis=1)], axis=1)
-        best_r = np.concatenate([best_r, part + lo], axis=1)
-    kk = min(k, best_s.shape[1])
-    order = np.lexsort((best_r, -best_s), axis=1)[:, :kk]
+        if lo == 0 and S.shape[1] >= kk:
+            part = np.argpartition(S, S.shape[1] - kk, axis=1)[:, S.shape[1] - kk:]
+            best_s = np.take_along_axis(S, part, axis=1)
+            best_r = part.astype(np.int64)
+            thr = best_s.min(axis=1)
+            continue
+        qi, ci = np.nonzero(S > thr[:, None])
+        if qi.size == 0:
+            continue
+        vals = S[qi, ci]
+        bounds = np.searchsorted(qi, np.arange(nq + 1))
+        for q in np.unique(qi):
+            a, b = bounds[q], bounds[q + 1]
+            s_all = np.concatenate([best_s[q], vals[a:b]])
+            r_all = np.concatenate([best_r[q], ci[a:b] + lo])
+            if s_all.size > kk:
+                sel = np.argpartition(s_all, s_all.size - kk)[s_all.size - kk:]
+                s_all, r_all = s_all[sel], r_all[sel]
+            best_s[q, :s_all.size], best_r[q, :r_all.size] = s_all, r_all
+            thr[q] = s_all.min() if s_all.size == kk else -np.inf
+    order = np.lexsort((best_r, -best_s), axis=1)
     return np.take_along_axis(best_r, order, axis=1), np.take_along_axis(best_s, order, axis=1)
