@@ -118,6 +118,41 @@ __device__ void bitonic_sort_desc(u64* sm, int P) {
     }
 }
 
+// Warp-level bitonic sort (descending) of 32*EPL keys held in registers: element e lives in lane e % 32,
+// register e / 32.  Strides >= 32 are register-to-register, smaller ones one shuffle.
+template <int EPL>
+__device__ __forceinline__ void warp_sort_desc(u64 (&k)[EPL], int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * EPL; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const int pr = r ^ jr;
+                    if (pr > r) {
+                        const bool desc = (((32 * r) & k2) == 0);   // k2 >= 64 here: the bit comes from r alone
+                        const u64 x = k[r], y = k[pr];
+                        const bool sw = desc ? (x < y) : (x > y);
+                        k[r] = sw ? y : x;
+                        k[pr] = sw ? x : y;
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const bool desc = (((lane + 32 * r) & k2) == 0);
+                    const u64 other = __shfl_xor_sync(0xffffffffu, k[r], j);
+                    const u64 mx = k[r] > other ? k[r] : other, mn = k[r] > other ? other : k[r];
+                    k[r] = (desc == lower) ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
 struct SelectArgs {
     u64* cand; int* cnt; int cap; u64* tau; int j_rank; int is_final; int kprime; int64_t n_rows;
     u64* topkeys; int* topn; float* bound; int* status; int dense_total; int nq;
@@ -157,6 +192,58 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     int P = 32;
     while (P < n) P <<= 1;
     u64* c = a.cand + (size_t)qq * a.cap;
+    // Intermediate level with many keys and a small rank j (the dense sparsest level: 1024-2048 keys, j ~ 16):
+    // no full sort.  The j-th largest of 64 strided group maxima is a lower bound P of the j-th largest key, the
+    // keys >= P (j..a few dozen) are compacted and sorted by one warp in registers.
+    if (!a.is_final && total <= a.cap && a.j_rank <= 32 && n >= 32 * a.j_rank) {
+        __shared__ u64 gmax64[64];
+        __shared__ u64 lst[256];
+        __shared__ int s_m;
+        __shared__ u64 s_P;
+        const int nt = blockDim.x, tid = threadIdx.x;
+        u64 lm = 0;
+        for (int i = tid; i < n; i += nt) { const u64 key = c[i]; lm = key > lm ? key : lm; }
+        sm[tid] = lm;
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        if (tid < 64) {
+            u64 g = 0;
+            for (int t2 = tid; t2 < nt; t2 += 64) g = sm[t2] > g ? sm[t2] : g;
+            gmax64[tid] = g;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            u64 k2[2] = {gmax64[lane], gmax64[lane + 32]};
+            warp_sort_desc<2>(k2, lane);
+            const int e = a.j_rank - 1;
+            const u64 p0 = __shfl_sync(0xffffffffu, k2[0], e & 31), p1 = __shfl_sync(0xffffffffu, k2[1], e & 31);
+            if (lane == 0) s_P = e < 32 ? p0 : p1;
+        }
+        __syncthreads();
+        const u64 P = s_P;
+        if (P != 0ull) {
+            for (int i = tid; i < n; i += nt) {
+                const u64 key = c[i];
+                if (key >= P) { const int pos = atomicAdd(&s_m, 1); if (pos < 256) lst[pos] = key; }
+            }
+        }
+        __syncthreads();
+        const int m = s_m;
+        if (P != 0ull && m <= 256) {            // m >= j_rank by construction
+            if (tid < 32) {
+                u64 k8[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) k8[r] = (lane + 32 * r) < m ? lst[lane + 32 * r] : 0ull;
+                warp_sort_desc<8>(k8, lane);
+                const int e = a.j_rank - 1;     // < 32: register 0
+                const u64 tj = __shfl_sync(0xffffffffu, k8[0], e);
+                if (lane < a.j_rank) c[lane] = k8[0];
+                if (lane == 0) { a.tau[qq] = tj; a.cnt[qq] = a.j_rank; }
+            }
+            return;
+        }
+        __syncthreads();                        // too many keys at the pivot (ties): full sort below
+    }
     if (threadIdx.x == 0) s_nz = 0;
     __syncthreads();
     int nz = 0;
