@@ -102,7 +102,8 @@ struct AvsScratch {
     int64_t* cid = nullptr;       // [nq, kprime] primary keys of the candidates
     double* out_s64 = nullptr;    // [nq, k] exact scores of the final hits (for the shard merge)
     // repair
-    int* flagged = nullptr;       // [1 + AVS_MAX_REPAIR_Q] count, then query indices
+    int* flagged = nullptr;       // [1 + nq] stage 1 (wide rescoring): count, then query indices
+    int* flagged2 = nullptr;      // [1 + AVS_MAX_REPAIR_Q] stage 2 (exact scan): count, then query indices
     double* rep_s = nullptr;      // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
     uint32_t* rep_row = nullptr;  // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
     int* rep_cnt = nullptr;       // [AVS_MAX_REPAIR_Q]

@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     } else {
         const int m = n < a.kprime ? n : a.kprime;
         for (int i = threadIdx.x; i < a.kprime; i += blockDim.x) a.topkeys[(size_t)qq * a.kprime + i] = i < m ? sm[i] : 0ull;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) c[i] = sm[i];   // sorted: the wide rescoring stage reads it
+        if (threadIdx.x == 0) a.cnt[qq] = total;
     }
     if (threadIdx.x == 0) select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1]);
 }
@@ -366,17 +368,98 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const float* __restrict_
         bool ok = n >= need;
         if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
         if (force_repair) ok = false;
-        if (!ok) {
+        if (!ok) {                                   // stage 1 of the repair: rescore the whole collected set
             const int pos = atomicAdd(flagged, 1);
-            if (pos < AVS_MAX_REPAIR_Q) {
-                flagged[1 + pos] = q;
-                rep_thr[pos] = (n >= need && need > 0) ? sm[need - 1].s : -INFINITY;
-                rep_cnt[pos] = 0;
-                status[q] |= ST_CERT_FAIL;
-            } else {
-                status[q] |= ST_CERT_FAIL | ST_UNCERTIFIED;
-                atomicAdd(dstat + 1, 1ull);
+            flagged[1 + pos] = q;
+            status[q] |= ST_CERT_FAIL;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Repair stage 1 (wide rescoring).  The final level left EVERY row whose scan key reached the last
+// threshold in the query's buffer (a few K' rows, sorted); the K' best were not enough to prove the
+// top-k, so rescore them all in float64.  Rows outside the buffer have scan score below the threshold
+// (or below the WIDE_MAX-th key), which is usually far under the k-th exact score: the certificate
+// passes without touching the rest of the database.  Otherwise the query moves on to the exact scan.
+// ---------------------------------------------------------------------------------------------
+#define AVS_WIDE_MAX 2048
+__global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restrict__ master, const int64_t* __restrict__ ids,
+                                                            const float* __restrict__ qraw, const double* __restrict__ qnorm,
+                                                            int dim, int metric, const u64* __restrict__ cand,
+                                                            const int* __restrict__ cnt, int cap, const u64* __restrict__ tau,
+                                                            const float* __restrict__ eps, int k, int64_t n_rows, int force_repair,
+                                                            int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                                                            int64_t* __restrict__ out_rows, double* __restrict__ out_s64,
+                                                            int* __restrict__ status, const int* __restrict__ flagged,
+                                                            int* __restrict__ flagged2, double* __restrict__ rep_thr,
+                                                            int* __restrict__ rep_cnt, u64* __restrict__ dstat) {
+    extern __shared__ unsigned char raw[];
+    Hit* sm = reinterpret_cast<Hit*>(raw);
+    const int nf = flagged[0];
+    const int f = blockIdx.x;
+    if (f >= nf) return;
+    const int q = flagged[1 + f];
+    const int total = cnt[q];
+    const bool lost = total > cap || (status[q] & ST_OVERFLOW);
+    int n = total < cap ? total : cap;
+    if (n > AVS_WIDE_MAX) n = AVS_WIDE_MAX;
+    const u64* c = cand + (size_t)q * cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int P = 32;
+    while (P < n) P <<= 1;
+    const double qn = qnorm[q];
+    const float* qp = qraw + (size_t)q * dim;
+    for (int i = warp; i < P; i += nwarps) {
+        Hit h;
+        if (i < n && !lost) {
+            h.row = avs_key_row(c[i]);
+            h.s = exact_score(master + (size_t)h.row * dim, qp, dim, qn, metric, lane);
+            h.id = ids[h.row];
+        } else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
+        if (lane == 0) sm[i] = h;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool desc = (i & k2) == 0;
+                    const Hit a = sm[i], b = sm[ixj];
+                    if (desc ? hit_better(b, a) : hit_better(a, b)) { sm[i] = b; sm[ixj] = a; }
+                }
             }
+            __syncthreads();
+        }
+    }
+    const int need = (int64_t)k < n_rows ? k : (int)n_rows;
+    // upper bound of the scan score of every row outside the rescored set
+    float b;
+    if ((int64_t)total >= n_rows) b = -INFINITY;
+    else if (total > n) b = avs_key_score(c[n - 1]);
+    else b = tau[q] == 0ull ? -INFINITY : avs_key_score(tau[q]);
+    bool ok = !lost && n >= need;
+    if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
+    if (force_repair > 1) ok = false;
+    if (ok) {
+        for (int t = threadIdx.x; t < k; t += blockDim.x) {
+            const bool valid = t < n;
+            out_ids[(size_t)q * k + t] = valid ? sm[t].id : -1;
+            out_scores[(size_t)q * k + t] = valid ? (float)sm[t].s : -INFINITY;
+            if (out_rows) out_rows[(size_t)q * k + t] = valid ? (int64_t)sm[t].row : -1;
+            out_s64[(size_t)q * k + t] = valid ? sm[t].s : -INFINITY;
+        }
+        if (threadIdx.x == 0) atomicAdd(dstat + 2, 1ull);
+    } else if (threadIdx.x == 0) {                   // stage 2: exact scan of the whole shard
+        const int pos = atomicAdd(flagged2, 1);
+        if (pos < AVS_MAX_REPAIR_Q) {
+            flagged2[1 + pos] = q;
+            rep_thr[pos] = (!lost && n >= need && need > 0) ? sm[need - 1].s : -INFINITY;
+            rep_cnt[pos] = 0;
+        } else {
+            status[q] |= ST_UNCERTIFIED;
+            atomicAdd(dstat + 1, 1ull);
         }
     }
 }
@@ -494,7 +577,7 @@ void avs_scratch_free(avs_store* s) {
     AvsScratch& c = s->sc;
     cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
-    cudaFree(c.s64); cudaFree(c.cid); cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.rep_s); cudaFree(c.rep_row);
+    cudaFree(c.s64); cudaFree(c.cid); cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.rep_s); cudaFree(c.rep_row);
     cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
     cudaFree(c.d_ids); cudaFree(c.d_scores); cudaFree(c.d_rows);
     if (c.h2d_q) cudaFree(c.h2d_q);
@@ -521,6 +604,7 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.tau, (size_t)nq2));
         AVS_CHECK(dev_alloc(&c.topn, (size_t)nq2));
         AVS_CHECK(dev_alloc(&c.status, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.flagged, (size_t)nq2 + 1));
     }
     if (grow_q || grow_cap) AVS_CHECK(dev_alloc(&c.cand, (size_t)nq2 * cap2));
     if (grow_q || grow_kp) {
@@ -529,8 +613,8 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.cid, (size_t)nq2 * kp2));
     }
     if (grow_q || grow_k) AVS_CHECK(dev_alloc(&c.out_s64, (size_t)nq2 * k2));
-    if (!c.flagged) {
-        AVS_CHECK(dev_alloc(&c.flagged, (size_t)1 + AVS_MAX_REPAIR_Q));
+    if (!c.flagged2) {
+        AVS_CHECK(dev_alloc(&c.flagged2, (size_t)1 + AVS_MAX_REPAIR_Q));
         AVS_CHECK(dev_alloc(&c.rep_s, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
         AVS_CHECK(dev_alloc(&c.rep_row, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
         AVS_CHECK(dev_alloc(&c.rep_cnt, (size_t)AVS_MAX_REPAIR_Q));
@@ -660,6 +744,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     s->st_last_path = use_gemm ? 2 : 1;
 
     AVS_CUDA(cudaMemsetAsync(c.flagged, 0, sizeof(int), st));
+    AVS_CUDA(cudaMemsetAsync(c.flagged2, 0, sizeof(int), st));
     const int n_slots = use_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
     prep_queries_kernel<<<n_slots, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
                                                 c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status);
@@ -671,6 +756,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         AVS_CUDA(cudaFuncSetAttribute(select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         AVS_CUDA(cudaFuncSetAttribute(repair_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(AVS_REPAIR_CAP * sizeof(Hit))));
+        AVS_CUDA(cudaFuncSetAttribute(wide_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(AVS_WIDE_MAX * sizeof(Hit))));
         attr_done = true;
     }
 
@@ -696,13 +783,19 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
                                         c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
-    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, c.flagged,
+    wide_rescore_kernel<<<nq, 1024, AVS_WIDE_MAX * sizeof(Hit), st>>>(
+        s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, use_gemm ? c.eps_gemm : c.eps_gemv, k,
+        s->count, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
+        c.rep_cnt, s->dstat);
+    s->st_launches++;
+    AVS_CUDA(cudaGetLastError());
+    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, c.flagged2,
                                                        c.rep_thr, c.rep_s, c.rep_row, c.rep_cnt);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     const int rep_blocks = nq < AVS_MAX_REPAIR_Q ? nq : AVS_MAX_REPAIR_Q;
     repair_finalize_kernel<<<rep_blocks, 1024, AVS_REPAIR_CAP * sizeof(Hit), st>>>(
-        c.flagged, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, s->count, out_ids, out_scores, out_rows, c.out_s64, c.status,
+        c.flagged2, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, s->count, out_ids, out_scores, out_rows, c.out_s64, c.status,
         s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
@@ -764,11 +857,11 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "last_levels") *out = s->st_last_levels;
     else if (k == "last_final_rows") *out = s->st_last_final_rows;
     else if (k == "last_scan_path") *out = s->st_last_path;
-    else if (k == "repaired_queries" || k == "uncertified_queries") {
+    else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries") {
         AVS_CUDA(cudaSetDevice(s->device));
-        u64 h[2];
+        u64 h[3];
         AVS_CUDA(cudaMemcpy(h, s->dstat, sizeof(h), cudaMemcpyDeviceToHost));
-        *out = (int64_t)(k == "repaired_queries" ? h[0] : h[1]);
+        *out = (int64_t)(k == "repaired_queries" ? h[0] : k == "uncertified_queries" ? h[1] : h[2]);
     } else { avs_set_error("avs_get_stat: unknown stat '%s'", key); return AVS_E_INVALID; }
     return AVS_OK;
 }

@@ -299,6 +299,7 @@ def run_ours(a):
                           "scan_path": path, "levels": levels, "kprime": st.stat("last_kprime")}
     unc = st.stat("uncertified_queries")
     rep = st.stat("repaired_queries")
+    wide = st.stat("wide_rescored_queries")
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -329,7 +330,8 @@ def run_ours(a):
                            "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],
                            "oversample_kprime": main["kprime"]},
                 "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
-                "cpu_baseline": cpu, "uncertified_queries": unc, "repaired_queries": rep}
+                "cpu_baseline": cpu, "uncertified_queries": unc, "repaired_queries": rep,
+                "wide_rescored_queries": wide}
         if 1 in results and a.batch != 1:
             b1 = results[1]
             line["batch1"] = {"value": b1["qps"], "unit": "queries/s", "ms_per_step": b1["ms"], "e2e": b1["e2e"],

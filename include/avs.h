@@ -105,11 +105,13 @@ int avs_comm_init(avs_store* s, const void* unique_id128, int rank, int world);
 int avs_search_sharded(avs_store* s, const float* q, int nq, int k,
                        int64_t* out_ids, float* out_scores, void* stream);
 
-/* Options: "scan_path" 0=auto 1=gemv 2=gemm; "oversample" K' override (0=auto);
- * "gemm_min_batch"; "levels_ratio"; "force_repair" (testing). */
+/* Options: "scan_path" 0=auto 1=gemv 2=gemm; "oversample" K' override (0=auto); "gemm_min_batch";
+ * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant); "force_repair" (testing: 1 = force the
+ * wide-rescoring stage, 2 = force the exact scan as well). */
 int avs_set_option(avs_store* s, const char* key, int64_t value);
-/* Counters since creation: "kernel_launches", "searches", "queries", "repaired_queries",
- * "uncertified_queries", "last_kprime", "last_levels", "last_scan_path". */
+/* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
+ * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
+ * "uncertified_queries", "last_kprime", "last_levels", "last_scan_path", "last_final_rows". */
 int avs_get_stat(avs_store* s, const char* key, int64_t* out);
 
 /* Timing hook for bench.py: when enabled, CUDA events bracket the dominant scan

@@ -132,7 +132,11 @@ def test_repair_path_is_exact(pkg):
     st = pkg.Store(d, "COSINE", capacity=n)
     try:
         st.insert(X, ids)
-        st.set_option("force_repair", 1)
+        st.set_option("force_repair", 1)                       # stage 1: wide rescoring of the collected set
+        got_ids, got_d = st.search(Q, k)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert st.stat("wide_rescored_queries") == nq and st.stat("repaired_queries") == 0
+        st.set_option("force_repair", 2)                       # stage 2: exact float64 scan of the whole store
         got_ids, got_d = st.search(Q, k)
         _check(got_ids, got_d, exp_ids, exp_d)
         assert st.stat("repaired_queries") == nq
