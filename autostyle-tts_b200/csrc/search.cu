@@ -244,6 +244,89 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         }
         __syncthreads();                        // too many keys at the pivot (ties): full sort below
     }
+    // Large collected sets (big K', many-row dense level): 8-pass byte-wise radix select of the rank-`want` key
+    // straight from L2 (O(n) per pass, no 64-128 KB of shared memory) and an unordered compaction of the keys
+    // above it.  Neither the next level nor the rescoring stage needs the survivors sorted.
+    if (n > 1024) {
+        __shared__ int hist[256];
+        __shared__ int s_sel[2];
+        __shared__ u64 lst[256];
+        __shared__ int s_m;
+        const int nt = blockDim.x, tid = threadIdx.x;
+        int n_real = n;
+        if (a.dense_total > 0) {                    // padding slots of the dense level hold key 0
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            int nzc = 0;
+            for (int i = tid; i < n; i += nt) nzc += c[i] != 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
+            if (lane == 0 && nzc) atomicAdd(&s_m, nzc);
+            __syncthreads();
+            n_real = s_m;
+            total = n_real;
+            __syncthreads();
+        }
+        int jj = a.j_rank;
+        if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
+        const int want = a.is_final ? (n_real < a.kprime ? n_real : a.kprime) : (n_real >= jj ? jj : n_real);
+        u64 prefix = 0, maskb = 0;
+        int rank = want - 1;
+        if (want > 0) {
+            for (int byte = 7; byte >= 0; --byte) {
+                for (int i = tid; i < 256; i += nt) hist[i] = 0;
+                __syncthreads();
+                for (int i0 = 0; i0 < n; i0 += nt) {      // whole warps stay converged for the match below
+                    const int i = i0 + tid;
+                    const u64 key = i < n ? c[i] : 0ull;
+                    const bool in = i < n && (key & maskb) == prefix;
+                    const int bin = in ? (int)((key >> (8 * byte)) & 0xFFull) : 256 + lane;   // non-members: unique dummies
+                    // scores share their leading bytes: aggregate equal bins inside the warp, one atomic per bin
+                    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                    if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+                }
+                __syncthreads();
+                if (tid < 32) {                     // lane l owns bins 255-8l .. 248-8l (descending key order)
+                    int loc[8], sum = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) { loc[b] = hist[255 - 8 * lane - b]; sum += loc[b]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+                    int accb = incl - sum;
+                    if (rank >= accb && rank < incl) {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            if (rank >= accb && rank < accb + loc[b]) { s_sel[0] = 255 - 8 * lane - b; s_sel[1] = accb; }
+                            accb += loc[b];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (u64)s_sel[0] << (8 * byte);
+                maskb |= 0xFFull << (8 * byte);
+                rank -= s_sel[1];
+            }
+        }
+        const u64 Pk = want > 0 ? prefix : ~0ull;   // the rank-(want-1) key; exactly `want` keys are >= it
+        if (tid == 0) s_m = 0;
+        if (a.is_final) for (int i = tid; i < a.kprime; i += nt) a.topkeys[(size_t)qq * a.kprime + i] = 0ull;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            const u64 key = c[i];
+            if (key >= Pk && key != 0ull) {
+                const int pos = atomicAdd(&s_m, 1);
+                if (a.is_final) { if (pos < a.kprime) a.topkeys[(size_t)qq * a.kprime + pos] = key; }
+                else if (pos < 256) lst[pos] = key;
+            }
+        }
+        __syncthreads();
+        if (!a.is_final) {
+            for (int i = tid; i < want && i < 256; i += nt) c[i] = lst[i];
+        } else if (tid == 0) a.cnt[qq] = total;
+        if (tid == 0) select_emit_scalar(a, qq, total, n_real, Pk, Pk);
+        return;
+    }
     if (threadIdx.x == 0) s_nz = 0;
     __syncthreads();
     int nz = 0;
@@ -383,7 +466,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const float* __restrict_
 // (or below the WIDE_MAX-th key), which is usually far under the k-th exact score: the certificate
 // passes without touching the rest of the database.  Otherwise the query moves on to the exact scan.
 // ---------------------------------------------------------------------------------------------
-#define AVS_WIDE_MAX 2048
+#define AVS_WIDE_MAX 4096
 __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restrict__ master, const int64_t* __restrict__ ids,
                                                             const float* __restrict__ qraw, const double* __restrict__ qnorm,
                                                             int dim, int metric, const u64* __restrict__ cand,
@@ -401,9 +484,9 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
     if (f >= nf) return;
     const int q = flagged[1 + f];
     const int total = cnt[q];
-    const bool lost = total > cap || (status[q] & ST_OVERFLOW);
-    int n = total < cap ? total : cap;
-    if (n > AVS_WIDE_MAX) n = AVS_WIDE_MAX;
+    // the buffer is not necessarily sorted: rescore all of it or hand the query to the exact scan
+    const bool lost = total > cap || total > AVS_WIDE_MAX || (status[q] & ST_OVERFLOW);
+    const int n = lost ? 0 : total;
     const u64* c = cand + (size_t)q * cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int P = 32;
@@ -437,7 +520,6 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
     // upper bound of the scan score of every row outside the rescored set
     float b;
     if ((int64_t)total >= n_rows) b = -INFINITY;
-    else if (total > n) b = avs_key_score(c[n - 1]);
     else b = tau[q] == 0ull ? -INFINITY : avs_key_score(tau[q]);
     bool ok = !lost && n >= need;
     if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
@@ -707,7 +789,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     int64_t strides[AVS_MAX_LEVELS];
     int L = 1;
     strides[0] = 1;
-    while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > cap && L < AVS_MAX_LEVELS) {
+    const int64_t level0_rows = cap < 2048 ? cap : 2048;   // the threshold-free level stays small whatever K' is
+    while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
         const int64_t r = (fine_levels && L <= 3) ? 4 : rho;
@@ -724,18 +807,24 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         lv[i].ratio = i == 0 ? 0 : lv[i].skip / stride;
         lv[i].n_visit = lv[i].ratio > 1 ? lv[i].n_iter - (lv[i].n_iter + lv[i].ratio - 1) / lv[i].ratio : lv[i].n_iter;
         lv[i].dense = (i == 0 && use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ? 1 : 0;
-        // rank whose key becomes the next threshold: expected survivors at the next level = j * ratio
-        int64_t j = 0;
-        if (i < L - 1) {
-            const int64_t ratio = stride / strides[L - 2 - i];
-            // expected survivors by the end of the next level
-            int64_t target;
-            if (fine_levels) target = ratio > 4 ? 8ll * kprime : ((i + 1 == L - 1) ? 4ll * kprime : 2ll * kprime);
-            else target = (i + 1 == L - 1) ? 8ll * kprime : 8ll * kprime;
-            j = target / ratio;
+        j_ranks[i] = 0;
+    }
+
+    // Threshold ranks, from the last level backwards.  The rank-j key of what level i has collected becomes the
+    // threshold of level i+1, which then ends with about j*ratio survivors (relative spread ~ 1/sqrt(j)).  The
+    // last threshold must leave at least K' rows with a wide margin: K' + 8*sqrt(K'*ratio) expected survivors
+    // (K'=32, x4: 128; K'=256, x4: 512); every earlier level must hold comfortably more keys than the rank the
+    // next select asks for.
+    {
+        double need = 0.0;
+        for (int i = L - 2; i >= 0; --i) {
+            const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
+            if (i == L - 2) need = (double)kprime + 8.0 * sqrt((double)kprime * ratio);
+            int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
+            j_ranks[i] = (int)j;
+            need = 1.5 * (double)j + 16.0;
         }
-        j_ranks[i] = (int)j;
     }
 
     s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;
