@@ -173,8 +173,8 @@ __device__ __forceinline__ void select_emit_scalar(const SelectArgs& a, int q, i
         float b;
         int st = 0;
         if (total > a.cap || (a.status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }   // lost entries
+        else if (n > a.kprime) b = avs_key_score(key_kp);                 // rows outside the K' candidates <= K'-th key
         else if ((int64_t)n >= a.n_rows) b = -INFINITY;                   // every row is a candidate
-        else if (n > a.kprime) b = avs_key_score(key_kp);                 // rows outside <= K'-th key
         else b = a.tau[q] == 0ull ? -INFINITY : avs_key_score(a.tau[q]);  // rows outside < threshold
         a.bound[q] = b;
         a.status[q] |= st;
@@ -537,7 +537,10 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
         const int pos = atomicAdd(flagged2, 1);
         if (pos < AVS_MAX_REPAIR_Q) {
             flagged2[1 + pos] = q;
-            rep_thr[pos] = (!lost && n >= need && need > 0) ? sm[need - 1].s : -INFINITY;
+            // lower bound of the true k-th score: from this stage if it rescored anything, else from finalize's
+            // K' candidates (out_s64 still holds their exact top-k)
+            rep_thr[pos] = (!lost && n >= need && need > 0) ? sm[need - 1].s
+                                                            : (need > 0 ? out_s64[(size_t)q * k + need - 1] : -INFINITY);
             rep_cnt[pos] = 0;
         } else {
             status[q] |= ST_UNCERTIFIED;

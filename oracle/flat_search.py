@@ -165,7 +165,8 @@ def search_large(X, ids, Q, k, metric="COSINE", slack=64, xnorm=None):
     """Same result as `search(accum="f64")` for big N: a BLAS float64 pass picks
     k+slack candidates per query, which are then re-evaluated with the
     deterministic per-row arithmetic and ordered exactly.  The BLAS scores differ
-    from the deterministic ones by ~1e-15, far below the slack window."""
+    from the deterministic ones by ~1e-15, far below the slack window.  NOT valid when
+    more than `slack` rows tie exactly with the k-th score (use `search` then)."""
     X = np.ascontiguousarray(X, dtype=np.float32)
     Q = np.atleast_2d(np.asarray(Q, dtype=np.float32))
     ids = np.asarray(ids, dtype=np.int64)

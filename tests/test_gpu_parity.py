@@ -357,3 +357,58 @@ def test_search_json_front_end_emits_the_tts_contract(pkg, f1, tmp_path):
         assert out[i]["retrieved_file_id"] == "/styles/" + meta[row]["file_id"] and out[i]["retrieved_text"] == meta[row]["text"]
         assert abs(out[i]["distance"] - float(kat["pert_dist"][i, 0])) <= RTOL
     assert out[6]["retrieved_file_id"] == "N/A" and out[6]["distance"] is None
+
+
+@pytest.mark.parametrize("nq", [2, 40])
+def test_adversarial_insertion_order_and_duplicate_blocks(pkg, nq):
+    """Data that defeats the sampled thresholds: rows sorted by similarity to the queries' direction, a contiguous
+    block of 3000 near-duplicates of one query (overflows the collection buffer) and 300 exact duplicates of
+    another with shuffled primary keys.  The answer must still be the oracle's (via the repair stages)."""
+    rng = np.random.default_rng(2024)
+    n, d, k = 40_000, 128, 10
+    base = rng.standard_normal(d).astype(np.float32)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X += np.linspace(3.0, -3.0, n, dtype=np.float32)[:, None] * base[None, :] / np.linalg.norm(base)   # sorted by <x, base>
+    hot = rng.standard_normal(d).astype(np.float32)
+    X[20_000:23_000] = hot[None, :] + 1e-3 * rng.standard_normal((3000, d)).astype(np.float32)         # near-duplicate block
+    dup = rng.standard_normal(d).astype(np.float32)
+    X[30_000:30_300] = dup                                                                             # exact duplicates
+    ids = rng.permutation(n).astype(np.int64)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    Q[0] = hot
+    Q[1] = dup * 3.0
+    if nq > 2:
+        Q[2] = base
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        got_ids, got_d = st.search(Q, k)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, k, "COSINE")    # per-row deterministic oracle: exact ties by id
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert sorted(got_ids[1].tolist()) == sorted(np.sort(ids[30_000:30_300])[:k].tolist())           # ties -> smallest ids
+        assert st.stat("uncertified_queries") == 0
+        assert st.stat("wide_rescored_queries") + st.stat("repaired_queries") >= 1                        # a repair stage ran
+    finally:
+        st.close()
+
+
+def test_fuzz_small_shapes_against_oracle(pkg):
+    """Seeded sweep over ragged shapes, both metrics, both scan paths."""
+    rng = np.random.default_rng(99)
+    for trial in range(40):
+        n = int(rng.integers(1, 3000)) if trial < 24 else int(rng.integers(3000, 90_000))
+        d = int(rng.choice([1, 3, 8, 17, 64, 100, 257, 512]))
+        nq = int(rng.integers(1, 70))
+        k = int(rng.choice([1, 2, 7, 10, 33, 100, 256]))
+        metric = "COSINE" if trial % 2 == 0 else "IP"
+        X, ids, Q = _data(n, d, nq, seed=1000 + trial, scale=(trial % 3 == 0))
+        st = pkg.Store(d, metric, capacity=max(1, n // 2))
+        try:
+            st.insert(X, ids)
+            st.set_option("scan_path", 1 + trial % 2 if nq <= 8 or trial % 2 else 0)
+            got_ids, got_d = st.search(Q, k)
+            exp_ids, exp_d, _ = fs.search(X, ids, Q, k, metric)
+            _check(got_ids, got_d, exp_ids, exp_d)
+            assert st.stat("uncertified_queries") == 0, (n, d, nq, k, metric)
+        finally:
+            st.close()
