@@ -150,6 +150,8 @@ struct avs_store {
     void* gemm_state = nullptr;
     // multi-GPU
     void* nccl_comm = nullptr;
+    void* p2p_state = nullptr;       // peer-memory exchange regions (comm.cu)
+    int opt_p2p = 1;
     int rank = 0, world = 1;
 };
 

@@ -103,6 +103,160 @@ __global__ void __launch_bounds__(256) shard_merge_kernel(const GatherItem* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused exchange + merge over NVLink peer memory (replaces pack -> ncclAllGather -> merge when connected).
+// Every rank exposes one exchange region through CUDA IPC.  One kernel per search, one CTA per query:
+//   1. store this rank's k (score, id) items of the query straight into slot [rank] of EVERY peer's region
+//      (remote stores over NVLink) and of its own,
+//   2. __threadfence_system, then publish flag[rank][q] = seq in every region,
+//   3. spin until the local region shows seq for the query from every rank,
+//   4. merge world*k items by (score desc, id asc) and write the global top-k.
+// A CTA pushes before it waits and never depends on another local CTA, so any scheduling order completes.
+// Two parities alternate between searches: a rank can only be one search ahead of its slowest peer (it needs
+// that peer's push to finish its own merge), so a region is never overwritten while it is still being read.
+// ---------------------------------------------------------------------------------------------
+#define P2P_MAX_WORLD 8
+#define P2P_ITEMS_PER_SRC (1 << 18)          // (score, id) items per source rank per parity (4 MiB)
+#define P2P_MAX_NQ (1 << 14)
+
+struct P2PRegion {                            // layout of one rank's exchange region
+    GatherItem items[2][P2P_MAX_WORLD][P2P_ITEMS_PER_SRC];
+    unsigned int flags[2][P2P_MAX_WORLD][P2P_MAX_NQ];
+    unsigned int timeouts;
+};
+struct P2PPeers { P2PRegion* r[P2P_MAX_WORLD]; };
+
+struct P2PState {
+    P2PRegion* local = nullptr;
+    P2PPeers peers{};
+    bool connected = false;
+    unsigned int seq = 0;
+};
+
+__global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers, int rank, int world, unsigned int seq,
+                                                                 int nq, int k, const double* __restrict__ s64,
+                                                                 int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    extern __shared__ unsigned char raw[];
+    GatherItem* sm = reinterpret_cast<GatherItem*>(raw);
+    const int q = blockIdx.x, par = seq & 1;
+    const size_t slot = (size_t)q * k;
+    // 1. push my items for this query into every region (mine included)
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int r = i / k, t = i - r * k;
+        GatherItem it;
+        it.s = s64[slot + t];
+        it.id = out_ids[slot + t];
+        peers.r[r]->items[par][rank][slot + t] = it;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish
+    if (threadIdx.x < world) {
+        volatile unsigned int* f = &peers.r[threadIdx.x]->flags[par][rank][q];
+        *f = seq;
+    }
+    // 3. wait for every rank's items of this query in MY region (bounded spin: a missing peer must not hang the GPU)
+    P2PRegion* mine = peers.r[rank];
+    if (threadIdx.x < world) {
+        volatile unsigned int* f = &mine->flags[par][threadIdx.x][q];
+        long long spins = 0;
+        while (*f != seq) {
+            if (++spins > (1ll << 28)) { atomicAdd(&mine->timeouts, 1u); break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    // 4. merge
+    const int total = world * k;
+    int P = 32;
+    while (P < total) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        GatherItem it;
+        if (i < total) {
+            const int r = i / k, t = i - r * k;
+            const volatile GatherItem* src = &mine->items[par][r][slot + t];
+            it.s = src->s;
+            it.id = src->id;
+            if (it.id == -1 && it.s == -INFINITY) it.id = INT64_MAX;
+        } else { it.s = -INFINITY; it.id = INT64_MAX; }
+        sm[i] = it;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool desc = (i & k2) == 0;
+                    const GatherItem a = sm[i], b = sm[ixj];
+                    if (desc ? item_better(b, a) : item_better(a, b)) { sm[i] = b; sm[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const GatherItem it = sm[t];
+        const bool pad = it.id == INT64_MAX && it.s == -INFINITY;
+        out_ids[slot + t] = pad ? -1 : it.id;
+        out_scores[slot + t] = pad ? -INFINITY : (float)it.s;
+    }
+}
+
+static void p2p_free(avs_store* s) {
+    P2PState* st = (P2PState*)s->p2p_state;
+    if (!st) return;
+    for (int r = 0; r < P2P_MAX_WORLD; ++r)
+        if (st->peers.r[r] && st->peers.r[r] != st->local) cudaIpcCloseMemHandle(st->peers.r[r]);
+    if (st->local) cudaFree(st->local);
+    cudaGetLastError();
+    delete st;
+    s->p2p_state = nullptr;
+}
+
+extern "C" int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out) {
+    if (!s || !handle64_out || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) { avs_set_error("avs_p2p_init: bad arguments (rank %d, world %d, max world %d)", rank, world, P2P_MAX_WORLD); return AVS_E_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    AVS_CUDA(cudaSetDevice(s->device));
+    p2p_free(s);
+    P2PState* st = new P2PState();
+    if (cudaMalloc((void**)&st->local, sizeof(P2PRegion)) != cudaSuccess) {
+        cudaGetLastError();
+        delete st;
+        avs_set_error("out of device memory for the peer exchange region (%zu bytes)", sizeof(P2PRegion));
+        return AVS_E_NOMEM;
+    }
+    AVS_CUDA(cudaMemset(st->local, 0, sizeof(P2PRegion)));
+    cudaIpcMemHandle_t h;
+    AVS_CUDA(cudaIpcGetMemHandle(&h, st->local));
+    memcpy(handle64_out, &h, sizeof(h));
+    s->p2p_state = st;
+    s->rank = rank;
+    s->world = world;
+    return AVS_OK;
+}
+
+extern "C" int avs_p2p_connect(avs_store* s, const void* handles, int world) {
+    if (!s || !handles || !s->p2p_state || world != s->world) { avs_set_error("avs_p2p_connect: call avs_p2p_init first (and pass the same world)"); return AVS_E_STATE; }
+    AVS_CUDA(cudaSetDevice(s->device));
+    P2PState* st = (P2PState*)s->p2p_state;
+    for (int r = 0; r < world; ++r) {
+        if (r == s->rank) { st->peers.r[r] = st->local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * r, sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            avs_set_error("cudaIpcOpenMemHandle for rank %d failed: %s (no peer access between these GPUs?)", r, cudaGetErrorString(e));
+            return AVS_E_CUDA;
+        }
+        st->peers.r[r] = (P2PRegion*)p;
+    }
+    st->connected = true;
+    return AVS_OK;
+}
+
 extern "C" int avs_nccl_unique_id(void* out128) {
     if (!out128) { avs_set_error("avs_nccl_unique_id: NULL buffer"); return AVS_E_INVALID; }
     AVS_CHECK(nccl_load());
@@ -129,6 +283,7 @@ extern "C" int avs_comm_init(avs_store* s, const void* unique_id128, int rank, i
 }
 
 void avs_comm_free(avs_store* s) {
+    p2p_free(s);
     if (s->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)s->nccl_comm);
     s->nccl_comm = nullptr;
     s->world = 1;
@@ -138,12 +293,25 @@ void avs_comm_free(avs_store* s) {
 extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
                                   void* stream) {
     if (!s) { avs_set_error("avs_search_sharded: NULL store"); return AVS_E_INVALID; }
-    if (!s->nccl_comm) { avs_set_error("avs_search_sharded: avs_comm_init has not been called on this store"); return AVS_E_STATE; }
+    P2PState* p2p = (P2PState*)s->p2p_state;
+    const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
+    if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
     cudaStream_t st = (cudaStream_t)stream;
     // local exact top-k; ids/scores land in the caller's buffers first and are then replaced
     AVS_CHECK(avs_search_local(s, q, nq, k, out_ids, out_scores, nullptr, st));
     if (nq == 0) return AVS_OK;
     AvsScratch& c = s->sc;
+    if (use_p2p) {
+        int P = 32;
+        while (P < s->world * k) P <<= 1;
+        p2p->seq += 1;
+        if (p2p->seq == 0) p2p->seq = 2;   // 0 is the "never written" value of the flags; keep the parity sequence
+        p2p_exchange_merge_kernel<<<nq, 256, (size_t)P * sizeof(GatherItem), st>>>(p2p->peers, s->rank, s->world, p2p->seq, nq, k,
+                                                                                 c.out_s64, out_ids, out_scores);
+        s->st_launches++;
+        AVS_CUDA(cudaGetLastError());
+        return AVS_OK;
+    }
     const size_t items = (size_t)nq * k;
     const size_t cap_items = (size_t)c.nq_cap * c.k_cap;  // sized from the scratch capacities
     if (!c.gather_send || c.gather_items < cap_items || c.world_cap < s->world) {

@@ -935,6 +935,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "levels_ratio") s->opt_ratio = (int)value;
     else if (k == "force_repair") s->opt_force_repair = (int)value;
     else if (k == "cta_group") s->opt_cta_group = value == 2 ? 2 : 1;
+    else if (k == "p2p_merge") s->opt_p2p = value != 0;
     else { avs_set_error("avs_set_option: unknown option '%s'", key); return AVS_E_INVALID; }
     return AVS_OK;
 }

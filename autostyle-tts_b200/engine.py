@@ -25,7 +25,7 @@ METRIC_NAMES = {0: "COSINE", 1: "IP"}
 ABI_SYMBOLS = (
     "avs_create", "avs_destroy", "avs_reserve", "avs_insert", "avs_fill_synthetic", "avs_count", "avs_dim",
     "avs_metric", "avs_get_rows", "avs_get_ids", "avs_search", "avs_search_host", "avs_nccl_unique_id",
-    "avs_comm_init", "avs_search_sharded", "avs_set_option", "avs_get_stat", "avs_scan_timing",
+    "avs_comm_init", "avs_search_sharded", "avs_p2p_init", "avs_p2p_connect", "avs_set_option", "avs_get_stat", "avs_scan_timing",
     "avs_last_error", "avs_version",
 )
 
@@ -70,6 +70,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "avs_nccl_unique_id": (i32, [vp]),
         "avs_comm_init": (i32, [vp, vp, i32, i32]),
         "avs_search_sharded": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+        "avs_p2p_init": (i32, [vp, i32, i32, vp]),
+        "avs_p2p_connect": (i32, [vp, vp, i32]),
         "avs_set_option": (i32, [vp, ctypes.c_char_p, i64]),
         "avs_get_stat": (i32, [vp, ctypes.c_char_p, ctypes.POINTER(i64)]),
         "avs_scan_timing": (i32, [vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(i64)]),
@@ -217,6 +219,18 @@ class Store:
             raise AvsError(-1, "ncclUniqueId must be 128 bytes")
         buf = ctypes.create_string_buffer(unique_id, 128)
         _check(self._lib, self._lib.avs_comm_init(self._h, buf, int(rank), int(world)))
+
+    def p2p_init(self, rank: int, world: int) -> bytes:
+        """Allocates this rank's peer exchange region; returns its 64-byte CUDA IPC handle."""
+        buf = ctypes.create_string_buffer(64)
+        _check(self._lib, self._lib.avs_p2p_init(self._h, int(rank), int(world), buf))
+        return buf.raw
+
+    def p2p_connect(self, handles: bytes, world: int):
+        if len(handles) != 64 * world:
+            raise AvsError(-1, "p2p_connect needs world x 64 bytes of IPC handles in rank order")
+        buf = ctypes.create_string_buffer(handles, len(handles))
+        _check(self._lib, self._lib.avs_p2p_connect(self._h, buf, int(world)))
 
     # -- knobs ---------------------------------------------------------------------------------
     def set_option(self, key: str, value: int):

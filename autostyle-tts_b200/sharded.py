@@ -35,13 +35,39 @@ class ShardedStore:
     """A Store holding this rank's shard plus the NCCL communicator for the merge."""
 
     def __init__(self, dim: int, metric: str, n_total: int, rank: int, world: int, device: Optional[int] = None,
-                 group=None):
+                 group=None, p2p: bool = True):
         self.rank, self.world, self.n_total = rank, world, n_total
         self.lo, self.hi = shard_range(n_total, rank, world)
         self.store = Store(dim, metric, capacity=max(self.hi - self.lo, 1), device=rank if device is None else device)
+        self.p2p = False
         if world > 1:
             uid = exchange_unique_id(Store.nccl_unique_id, rank, group)
             self.store.comm_init(uid, rank, world)
+            if p2p and world <= 8:
+                self.p2p = self._connect_peers(group)
+
+    def _connect_peers(self, group) -> bool:
+        """Exchange the CUDA IPC handles of the peer exchange regions; all ranks agree on the outcome
+        (NCCL all-gather stays the exchange when any pair of GPUs has no peer access)."""
+        import torch.distributed as dist
+        from .engine import AvsError
+        try:
+            mine = self.store.p2p_init(self.rank, self.world)
+        except AvsError:
+            mine = None
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                self.store.p2p_connect(b"".join(handles), self.world)
+            except AvsError:
+                ok = False
+        votes = [None] * self.world
+        dist.all_gather_object(votes, ok, group=group)
+        ok = all(votes)
+        self.store.set_option("p2p_merge", 1 if ok else 0)
+        return ok
 
     def fill_synthetic(self, seed: int):
         """Rank-local slice of the global synthetic stream; ids are global row numbers."""

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--scan-path", type=int, default=0, help="0 auto, 1 gemv, 2 gemm")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--only-batch", action="store_true", help="skip the extra batch-1 measurement")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather + merge instead of the fused peer-memory kernel")
     return ap.parse_args()
 
 
@@ -202,7 +203,7 @@ def run_ours(a):
     tc_peak = float(peaks.get("bf16_tflops", 1590.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
-    ss = sharded.ShardedStore(a.dim, a.metric, a.rows, rank, world, device=local)
+    ss = sharded.ShardedStore(a.dim, a.metric, a.rows, rank, world, device=local, p2p=not a.no_p2p)
     st = ss.store
     ss.fill_synthetic(SEED_DB)
     st.set_option("scan_path", a.scan_path)
@@ -325,6 +326,7 @@ def run_ours(a):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k, "batch": a.batch,
                            "metric_type": a.metric, "sharding": f"rows/{world}" if world > 1 else "none",
+                           "exchange": ("fused peer-memory push+merge kernel (NVLink P2P)" if ss.p2p else "ncclAllGather + merge") if world > 1 else None,
                            "l2_policy": f"inputs larger than L2: the scan streams {rows_local * dpad * 2 / 1e6:.0f} MB of bf16 rows per step (L2 126 MB)",
                            "arith": "bf16 operands, fp32 accumulate scan; float64 rescoring of the candidates",
                            "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],

@@ -104,9 +104,16 @@ int avs_comm_init(avs_store* s, const void* unique_id128, int rank, int world);
  * id i64) -> merge by (score desc, id asc); every rank receives the global result. */
 int avs_search_sharded(avs_store* s, const float* q, int nq, int k,
                        int64_t* out_ids, float* out_scores, void* stream);
+/* Optional fused exchange over NVLink peer memory (replaces the ncclAllGather + merge of
+ * avs_search_sharded by ONE kernel that stores each rank's top-k straight into its peers' memory, flags
+ * it, waits for the peers' items and merges).  avs_p2p_init allocates this rank's exchange region and
+ * returns its 64-byte cudaIpcMemHandle; the caller all-gathers the handles (world x 64 bytes, rank order)
+ * and passes them to avs_p2p_connect.  world <= 8, nq*k <= 262144 per call (larger calls use NCCL). */
+int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out);
+int avs_p2p_connect(avs_store* s, const void* handles, int world);
 
 /* Options: "scan_path" 0=auto 1=gemv 2=gemm; "oversample" K' override (0=auto); "gemm_min_batch";
- * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant); "force_repair" (testing: 1 = force the
+ * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant); "p2p_merge" 0|1; "force_repair" (testing: 1 = force the
  * wide-rescoring stage, 2 = force the exact scan as well). */
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate

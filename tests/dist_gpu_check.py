@@ -35,16 +35,23 @@ def main():
         ss = sharded.ShardedStore(d, metric, n, rank, world, device=local)
         ss.fill_synthetic(42)
         Q = synth.planted_queries(43, 42, n, nq, d)
-        ids, sc = ss.search(torch.from_numpy(Q).cuda(), k)
-        ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+        qd = torch.from_numpy(Q).cuda()
         X = np.concatenate([synth.synth_rows(42, lo, min(50_000, n - lo), d) for lo in range(0, n, 50_000)])
         exp_ids, exp_d, _ = fs.search_large(X, np.arange(n), Q, k, metric)
-        good = np.array_equal(ids, exp_ids) and np.all(np.abs(sc - exp_d) <= 1e-5 * np.maximum(1, np.abs(exp_d)))
-        flag = torch.tensor([1 if good else 0], device="cuda")
+        flag = torch.tensor([1], device="cuda")
+        modes = (("p2p", 1), ("nccl", 0)) if ss.p2p else (("nccl", 0),)
+        for name, val in modes:                       # fused peer-memory exchange+merge, then ncclAllGather + merge
+            ss.store.set_option("p2p_merge", val)
+            for rep in range(3):                      # repeated searches exercise the alternating exchange buffers
+                ids, sc = ss.search(qd, k)
+            ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+            good = np.array_equal(ids, exp_ids) and np.all(np.abs(sc - exp_d) <= 1e-5 * np.maximum(1, np.abs(exp_d)))
+            if not good:
+                flag.zero_()
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(f"world={world} n={n} d={d} nq={nq} k={k} {metric}: {'OK' if flag.item() else 'MISMATCH'} "
-                  f"(shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
+                  f"(modes {[m[0] for m in modes]}, shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
                   f"uncertified {ss.store.stat('uncertified_queries')})", flush=True)
         ok &= bool(flag.item())
         ss.close()
