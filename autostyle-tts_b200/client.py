@@ -30,6 +30,7 @@ import numpy as np
 
 from . import milvus_lite_db as mldb
 from .engine import AvsError, Store
+from .filter_expr import compile_filter
 from .schema import CollectionSchema, DataType, FieldSchema, IndexParams, MilvusException
 
 MAX_LIMIT = 256  # largest `limit` the fused top-k pipeline serves (avs.h)
@@ -276,8 +277,6 @@ class MilvusClient:
         coll = self._coll(collection_name)
         if data is None:
             raise MilvusException("search needs `data` (one query vector or a list of them)")
-        if filter not in (None, ""):
-            raise MilvusException("filter expressions are not supported by this store yet (pass filter=None)")
         if anns_field not in (None, "", coll.vec_name):
             raise MilvusException(f"failed to get field schema by name: fieldName({anns_field}) not found")
         want = kwargs.pop("metric_type", None) or (search_params or {}).get("metric_type") or (kwargs.get("param") or {}).get("metric_type")
@@ -292,17 +291,25 @@ class MilvusClient:
         if n_rows == 0:
             return [[] for _ in range(nq)]
         store = self._ensure_store(coll)
+        mask = self._filter_mask(coll, filter)      # scalar expression -> row bitmap applied inside the scan
+        if mask is not None and not mask.any():
+            return [[] for _ in range(nq)]
         k = limit
-        while True:
-            try:
+        try:
+            if mask is not None:
+                store.set_filter(mask)
+            while True:
                 _, dist, rows = store.search(q, min(k, MAX_LIMIT), return_rows=True)
-            except AvsError as e:
-                raise MilvusException(e.message, e.code) from e
-            if not self.dedup_pk or k >= min(n_rows, MAX_LIMIT):
-                break
-            if all(len({coll.pks[r] for r in rows[i] if r >= 0}) >= min(limit, n_rows) for i in range(nq)):
-                break
-            k = min(k * 2, MAX_LIMIT)
+                if not self.dedup_pk or k >= min(n_rows, MAX_LIMIT):
+                    break
+                if all(len({coll.pks[r] for r in rows[i] if r >= 0}) >= min(limit, n_rows) for i in range(nq)):
+                    break
+                k = min(k * 2, MAX_LIMIT)
+        except AvsError as e:
+            raise MilvusException(e.message, e.code) from e
+        finally:
+            if mask is not None:
+                store.set_filter(None)
         names = self._resolve_output_fields(coll, output_fields)
         fetch_vec = coll.vec_name in names
         out: List[List[Dict[str, Any]]] = []
@@ -370,19 +377,37 @@ class MilvusClient:
               ids: Optional[Union[list, str, int]] = None, limit: Optional[int] = None, **kwargs) -> List[Dict[str, Any]]:
         if ids is not None:
             res = self.get(collection_name, ids, output_fields)
-        elif filter in (None, ""):
+        else:
             coll = self._coll(collection_name)
             names = self._resolve_output_fields(coll, output_fields if output_fields is not None else ["*"])
+            mask = self._filter_mask(coll, filter)
             res = []
-            for r, pk in enumerate(coll.pks[: limit if limit is not None else len(coll.pks)]):
+            for r, pk in enumerate(coll.pks):
+                if mask is not None and not mask[r]:
+                    continue
                 ent = {coll.pk_name: pk}
                 ent.update({k: v for k, v in coll.meta[r].items() if k in names})
                 res.append(ent)
-        else:
-            raise MilvusException("filter expressions are not supported by this store yet")
+                if limit is not None and len(res) >= limit:
+                    break
         return res[:limit] if limit is not None else res
 
     # ------------------------------------------------------------------ internals
+    @staticmethod
+    def _filter_mask(coll: _Collection, expr: Optional[str]) -> Optional[np.ndarray]:
+        """Evaluates a scalar filter expression over the host-side fields -> bool mask per row (None = no filter)."""
+        if expr in (None, ""):
+            return None
+        if not isinstance(expr, str):
+            raise MilvusException(f"wrong type of argument 'filter', expected 'str', got '{type(expr).__name__}'")
+        pred = compile_filter(expr)
+        mask = np.zeros(len(coll.pks), dtype=bool)
+        for r, pk in enumerate(coll.pks):
+            fields = dict(coll.meta[r])
+            fields[coll.pk_name] = pk
+            mask[r] = pred(fields)
+        return mask
+
     def _coll(self, name: str) -> _Collection:
         c = self._colls.get(name)
         if c is None:

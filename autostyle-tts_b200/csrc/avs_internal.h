@@ -98,8 +98,6 @@ struct AvsScratch {
     u64* topkeys = nullptr;       // [nq, kprime] final bf16-scan candidates, sorted desc
     int* topn = nullptr;          // [nq]
     int* status = nullptr;        // [nq] bit0 overflow, bit1 underflow, bit2 cert failed, bit3 uncertified
-    double* s64 = nullptr;        // [nq, kprime] exact scores of the candidates
-    int64_t* cid = nullptr;       // [nq, kprime] primary keys of the candidates
     double* out_s64 = nullptr;    // [nq, k] exact scores of the final hits (for the shard merge)
     // repair
     int* flagged = nullptr;       // [1 + nq] stage 1 (wide rescoring): count, then query indices
@@ -132,6 +130,9 @@ struct avs_store {
     __nv_bfloat16* xb = nullptr;      // [capacity, dpad] bf16 scan copy (unit rows for COSINE)
     float* inv_norm = nullptr;        // [capacity] 1/||x|| (0 for zero rows)
     int64_t* ids = nullptr;           // [capacity]
+    uint32_t* filter = nullptr;       // optional row bitmap (bit r set = row r may be returned), set by avs_set_filter
+    int64_t filter_allowed = 0;       // number of set bits
+    size_t filter_words = 0;          // allocated words
     float* gstat = nullptr;           // [4] device scalars: r_max, xnorm_max (non-negative, atomicMax on bits)
     unsigned long long* dstat = nullptr;  // [8] device counters: repaired, uncertified
     AvsScratch sc;
@@ -156,7 +157,6 @@ struct avs_store {
 };
 
 // ---- host entry points implemented across translation units ----------------------------------
-int avs_launch_prep(avs_store* s, const float* q, int nq, cudaStream_t st);
 int avs_launch_scan_gemv(avs_store* s, int q0, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
 int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
 void avs_gemm_state_free(avs_store* s);

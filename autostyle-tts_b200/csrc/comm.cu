@@ -296,6 +296,7 @@ extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, i
     P2PState* p2p = (P2PState*)s->p2p_state;
     const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
     if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
+    if (s->filter) { avs_set_error("avs_search_sharded: row filters are not supported on a sharded store"); return AVS_E_STATE; }
     cudaStream_t st = (cudaStream_t)stream;
     // local exact top-k; ids/scores land in the caller's buffers first and are then replaced
     AVS_CHECK(avs_search_local(s, q, nq, k, out_ids, out_scores, nullptr, st));

@@ -61,7 +61,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -128,17 +127,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PipeState {
@@ -152,7 +140,7 @@ template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  int64_t n_rows, int n_qblocks, int num_k_blocks, AvsLevel lv, const u64* __restrict__ tau,
-                 u64* __restrict__ cand, int* __restrict__ cnt, int cap) {
+                 u64* __restrict__ cand, int* __restrict__ cnt, int cap, const uint32_t* __restrict__ filt) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -302,7 +290,11 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     u64* dst = my_cand + (size_t)m * BLOCK_N + half * 128 + col0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        dst[i] = (col0 + i < valid_cols && tau_k != ~0ull) ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
+                    {
+                        const uint32_t row = (uint32_t)(row0 + col0 + i);
+                        const bool keep = col0 + i < valid_cols && tau_k != ~0ull && (!filt || ((filt[row >> 5] >> (row & 31)) & 1u));
+                        dst[i] = keep ? avs_make_key(__uint_as_float(v[i]), row) : 0ull;
+                    }
                     return;
                 }
                 float gm[4];
@@ -343,8 +335,11 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     if ((sub >> (8 * gi + i)) & 1) {
-                                        my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), (uint32_t)(row0 + col0 + 8 * gi + i));
-                                        ++n_stash;
+                                        const uint32_t row = (uint32_t)(row0 + col0 + 8 * gi + i);
+                                        if (!filt || ((filt[row >> 5] >> (row & 31)) & 1u)) {
+                                            my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), row);
+                                            ++n_stash;
+                                        }
                                     }
                                 }
                             }
@@ -454,7 +449,7 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     AVS_CUDA(cudaLaunchKernelEx(&cfg, scan_gemm_kernel<CG>, mq, mx, s->count, n_qblocks, s->dpad / BLOCK_K, lv,
-                                (const u64*)s->sc.tau, s->sc.cand, s->sc.cnt, cap));
+                                (const u64*)s->sc.tau, s->sc.cand, s->sc.cnt, cap, (const uint32_t*)s->filter));
     s->st_launches++;
     return AVS_OK;
 }

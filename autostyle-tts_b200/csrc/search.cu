@@ -556,7 +556,8 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) repair_scan_kernel(const float* __restrict__ master, const float* __restrict__ q,
                                                           const double* __restrict__ qnorm, int64_t n_rows, int dim,
-                                                          int metric, const int* __restrict__ flagged,
+                                                          int metric, const uint32_t* __restrict__ filt,
+                                                          const int* __restrict__ flagged,
                                                           const double* __restrict__ rep_thr, double* __restrict__ rep_s,
                                                           uint32_t* __restrict__ rep_row, int* __restrict__ rep_cnt) {
     int nf = flagged[0];
@@ -570,6 +571,7 @@ __global__ void __launch_bounds__(256) repair_scan_kernel(const float* __restric
         const double thr = rep_thr[f], qn = qnorm[qi];
         const float* qp = q + (size_t)qi * dim;
         for (int64_t r = warp; r < n_rows; r += nwarps) {
+            if (filt && !((filt[r >> 5] >> (r & 31)) & 1u)) continue;
             const double s = exact_score(master + (size_t)r * dim, qp, dim, qn, metric, lane);
             if (lane == 0 && s >= thr) {
                 const int pos = atomicAdd(rep_cnt + f, 1);
@@ -662,7 +664,7 @@ void avs_scratch_free(avs_store* s) {
     AvsScratch& c = s->sc;
     cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
-    cudaFree(c.s64); cudaFree(c.cid); cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.rep_s); cudaFree(c.rep_row);
+    cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.rep_s); cudaFree(c.rep_row);
     cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
     cudaFree(c.d_ids); cudaFree(c.d_scores); cudaFree(c.d_rows);
     if (c.h2d_q) cudaFree(c.h2d_q);
@@ -694,8 +696,6 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
     if (grow_q || grow_cap) AVS_CHECK(dev_alloc(&c.cand, (size_t)nq2 * cap2));
     if (grow_q || grow_kp) {
         AVS_CHECK(dev_alloc(&c.topkeys, (size_t)nq2 * kp2));
-        AVS_CHECK(dev_alloc(&c.s64, (size_t)nq2 * kp2));
-        AVS_CHECK(dev_alloc(&c.cid, (size_t)nq2 * kp2));
     }
     if (grow_q || grow_k) AVS_CHECK(dev_alloc(&c.out_s64, (size_t)nq2 * k2));
     if (!c.flagged2) {
@@ -773,7 +773,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     AvsScratch& c = s->sc;
     float* bound = g_bound_of(c);
 
-    if (s->count == 0) {
+    const int64_t n_eff = s->filter ? s->filter_allowed : s->count;   // rows that may be returned
+    if (s->count == 0 || n_eff == 0) {
         const int64_t n = (int64_t)nq * k;
         fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_ids, out_scores, out_rows, c.out_s64, n);
         s->st_launches++;
@@ -863,7 +864,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
         }
         if (timed) timing_end(s, st, slot);
-        SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, s->count, c.topkeys, c.topn,
+        SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, n_eff, c.topkeys, c.topn,
                          bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq};
         select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
@@ -871,23 +872,23 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     }
 
     finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, use_gemm ? c.eps_gemm : c.eps_gemv, kprime, k,
-                                        s->count, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
+                                        n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
                                         c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     wide_rescore_kernel<<<nq, 1024, AVS_WIDE_MAX * sizeof(Hit), st>>>(
         s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, use_gemm ? c.eps_gemm : c.eps_gemv, k,
-        s->count, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
+        n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
         c.rep_cnt, s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
-    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, c.flagged2,
+    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, s->filter, c.flagged2,
                                                        c.rep_thr, c.rep_s, c.rep_row, c.rep_cnt);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     const int rep_blocks = nq < AVS_MAX_REPAIR_Q ? nq : AVS_MAX_REPAIR_Q;
     repair_finalize_kernel<<<rep_blocks, 1024, AVS_REPAIR_CAP * sizeof(Hit), st>>>(
-        c.flagged2, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, s->count, out_ids, out_scores, out_rows, c.out_s64, c.status,
+        c.flagged2, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, n_eff, out_ids, out_scores, out_rows, c.out_s64, c.status,
         s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());

@@ -209,6 +209,7 @@ __global__ void iota_ids_kernel(int64_t* ids, int64_t row0, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+extern "C" int avs_set_filter(avs_store* s, const uint32_t* bitmap_host, int64_t n_bits);
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static int alloc_arrays(avs_store* s, int64_t cap, float** master, __nv_bfloat16** xb, float** inv,
@@ -273,6 +274,7 @@ extern "C" int avs_destroy(avs_store* s) {
     cudaFree(s->inv_norm);
     cudaFree(s->ids);
     cudaFree(s->gstat);
+    cudaFree(s->filter);
     cudaFree(s->dstat);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     cudaGetLastError();
@@ -332,6 +334,7 @@ extern "C" int avs_insert(avs_store* s, const float* rows, const int64_t* ids, i
     if (n == 0) return AVS_OK;
     if (s->count + n > 0xFFFFFFF0ll) { avs_set_error("avs_insert: more than 2^32 rows per store"); return AVS_E_NOMEM; }
     AVS_CUDA(cudaSetDevice(s->device));
+    if (s->filter) AVS_CHECK(avs_set_filter(s, nullptr, 0));   // a row bitmap is only valid for the rows it was built on
     cudaStream_t st = (cudaStream_t)stream;
     if (s->count + n > s->capacity) {
         int64_t want = s->capacity * 2 > s->count + n ? s->capacity * 2 : s->count + n;
@@ -359,6 +362,7 @@ extern "C" int avs_fill_synthetic(avs_store* s, uint64_t seed, int64_t first_row
     if (n == 0) return AVS_OK;
     if (s->count + n > 0xFFFFFFF0ll) { avs_set_error("avs_fill_synthetic: more than 2^32 rows per store"); return AVS_E_NOMEM; }
     AVS_CUDA(cudaSetDevice(s->device));
+    if (s->filter) AVS_CHECK(avs_set_filter(s, nullptr, 0));
     cudaStream_t st = (cudaStream_t)stream;
     if (s->count + n > s->capacity) AVS_CHECK(avs_reserve(s, s->count + n));
     const int64_t row0 = s->count;
@@ -371,6 +375,34 @@ extern "C" int avs_fill_synthetic(avs_store* s, uint64_t seed, int64_t first_row
     AVS_CUDA(cudaGetLastError());
     AVS_CHECK(launch_normalize(s, row0, n, st));
     s->count += n;
+    return AVS_OK;
+}
+
+extern "C" int avs_set_filter(avs_store* s, const uint32_t* bitmap_host, int64_t n_bits) {
+    if (!s) { avs_set_error("avs_set_filter: NULL store"); return AVS_E_INVALID; }
+    AVS_CUDA(cudaSetDevice(s->device));
+    if (!bitmap_host) {                               // clear: every row may be returned again
+        s->filter_allowed = 0;
+        if (s->filter) { AVS_CUDA(cudaDeviceSynchronize()); cudaFree(s->filter); s->filter = nullptr; s->filter_words = 0; }
+        return AVS_OK;
+    }
+    if (n_bits != s->count) { avs_set_error("avs_set_filter: bitmap has %lld bits, the store %lld rows", (long long)n_bits, (long long)s->count); return AVS_E_INVALID; }
+    const size_t words = (size_t)((n_bits + 31) / 32);
+    AVS_CUDA(cudaDeviceSynchronize());
+    if (words > s->filter_words || !s->filter) {
+        cudaFree(s->filter);
+        s->filter = nullptr;
+        if (cudaMalloc((void**)&s->filter, (words ? words : 1) * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->filter_words = 0; avs_set_error("out of device memory for the filter bitmap"); return AVS_E_NOMEM; }
+        s->filter_words = words ? words : 1;
+    }
+    int64_t allowed = 0;
+    for (size_t w = 0; w < words; ++w) {
+        uint32_t v = bitmap_host[w];
+        if (w == words - 1 && (n_bits & 31)) v &= (1u << (n_bits & 31)) - 1;
+        allowed += __builtin_popcount(v);
+    }
+    AVS_CUDA(cudaMemcpy(s->filter, bitmap_host, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    s->filter_allowed = allowed;
     return AVS_OK;
 }
 

@@ -24,7 +24,7 @@ METRIC_NAMES = {0: "COSINE", 1: "IP"}
 # every symbol include/avs.h declares; tests check the built library exports all of them
 ABI_SYMBOLS = (
     "avs_create", "avs_destroy", "avs_reserve", "avs_insert", "avs_fill_synthetic", "avs_count", "avs_dim",
-    "avs_metric", "avs_get_rows", "avs_get_ids", "avs_search", "avs_search_host", "avs_nccl_unique_id",
+    "avs_metric", "avs_get_rows", "avs_get_ids", "avs_set_filter", "avs_search", "avs_search_host", "avs_nccl_unique_id",
     "avs_comm_init", "avs_search_sharded", "avs_p2p_init", "avs_p2p_connect", "avs_set_option", "avs_get_stat", "avs_scan_timing",
     "avs_last_error", "avs_version",
 )
@@ -65,6 +65,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "avs_metric": (i32, [vp]),
         "avs_get_rows": (i32, [vp, i64, i64, vp, vp]),
         "avs_get_ids": (i32, [vp, i64, i64, vp, vp]),
+        "avs_set_filter": (i32, [vp, vp, i64]),
         "avs_search": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "avs_search_host": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "avs_nccl_unique_id": (i32, [vp]),
@@ -205,6 +206,17 @@ class Store:
         _check(self._lib, self._lib.avs_search_host(self._h, q.ctypes.data, nq, int(k), ids.ctypes.data, sc.ctypes.data,
                                                     rows.ctypes.data))
         return (ids, sc, rows) if return_rows else (ids, sc)
+
+    def set_filter(self, mask):
+        """mask: bool array with one entry per stored row (True = may be returned), or None to clear."""
+        if mask is None:
+            _check(self._lib, self._lib.avs_set_filter(self._h, None, 0))
+            return
+        m = np.ascontiguousarray(np.asarray(mask, dtype=bool)).reshape(-1)
+        bits = np.packbits(m, bitorder="little")
+        words = np.zeros((m.shape[0] + 31) // 32 * 4, dtype=np.uint8)
+        words[: bits.shape[0]] = bits
+        _check(self._lib, self._lib.avs_set_filter(self._h, words.ctypes.data, int(m.shape[0])))
 
     # -- multi-GPU -----------------------------------------------------------------------------
     @staticmethod

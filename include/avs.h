@@ -89,6 +89,12 @@ int avs_get_ids(avs_store* s, int64_t first, int64_t n, int64_t* out, void* stre
 int avs_search(avs_store* s, const float* q, int nq, int k,
                int64_t* out_ids, float* out_scores, int64_t* out_rows, void* stream);
 
+/* Replaces the `filter=` argument of `MilvusClient.search` (/root/reference/milvus/RAG.py:387; always None in the
+ * reference): `bitmap_host` holds one bit per stored row (bit r of word r/32), set = the row may be returned.  The
+ * host evaluates the scalar expression on its metadata; the scan kernels test the bit on their (rare) accept
+ * path, so thresholds, certificate and repair all see the allowed rows only.  NULL clears the filter. */
+int avs_set_filter(avs_store* s, const uint32_t* bitmap_host, int64_t n_bits);
+
 /* Same search end to end from HOST buffers: H2D of the queries, the device pipeline,
  * D2H of ids/scores/rows, synchronised on return.  This is the call the Python
  * MilvusClient drop-in makes for list / ndarray queries. */

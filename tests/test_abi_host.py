@@ -177,3 +177,20 @@ def test_product_reader_opens_the_reference_shipped_db(f1):
         assert c.get_collection_stats("embeddings_biographies_collection")["row_count"] == 130
         assert c.describe_collection("embeddings_biographies_collection")["metric_type"] == "COSINE"
         c.close()
+
+
+def test_filter_expression_compiler():
+    fe = load_pkg("filter_expr")
+    pkg = load_pkg()
+    rows = [{"id": 1, "speaker": "emma", "file_id": "tonight1_a.wav", "n": 3},
+            {"id": 2, "speaker": "conan", "file_id": "emma_conan_b.wav", "n": 7}, {"id": 3, "file_id": "x.wav"}]
+    cases = {'speaker == "emma"': [True, False, False], "id in [2,3] and n > 5": [False, True, False],
+             'file_id like "tonight1%"': [True, False, False], 'not (speaker == "emma") || id == 1': [True, True, True],
+             'n % 2 == 1 && id >= 1': [True, True, False], '$meta["speaker"] != "emma"': [False, True, False],
+             'file_id like "%.wav" and ! (id == 2)': [True, False, True], "id NOT IN [1]": [False, True, True]}
+    for expr, want in cases.items():
+        pred = fe.compile_filter(expr)
+        assert [pred(r) for r in rows] == want, expr
+    for bad in ['__import__("os")', "id == 1; 2", 'speaker.lower() == "x"', "(lambda: 1)()", "id ==", "id = 1"]:
+        with pytest.raises(pkg.MilvusException):
+            fe.compile_filter(bad)

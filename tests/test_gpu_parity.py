@@ -412,3 +412,38 @@ def test_fuzz_small_shapes_against_oracle(pkg):
             assert st.stat("uncertified_queries") == 0, (n, d, nq, k, metric)
         finally:
             st.close()
+
+
+def test_scalar_filter_expressions(pkg):
+    """`filter=` (always None in the reference) evaluated on the host fields, applied as a
+    row bitmap inside the scan; equals the oracle run on the allowed rows only."""
+    rng = np.random.default_rng(8)
+    n, d = 5000, 96
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    speakers = ["emma", "conan", "tonight"]
+    c = pkg.MilvusClient(":memory:")
+    c.create_collection("f", dimension=d)
+    c.insert("f", [{"id": i, "vector": V[i], "speaker": speakers[i % 3], "dur": float(i % 17), "file_id": f"{speakers[i % 3]}_{i}.wav"}
+                   for i in range(n)])
+    Q = V[[5, 77, 4001]] + 0.01 * rng.standard_normal((3, d)).astype(np.float32)
+    for expr, keep in [('speaker == "emma"', np.arange(n) % 3 == 0),
+                       ('speaker in ["conan", "tonight"] and dur >= 5', (np.arange(n) % 3 != 0) & (np.arange(n) % 17 >= 5)),
+                       ('file_id like "tonight_4%" || id < 10', np.array([(i % 3 == 2 and str(i).startswith("4")) or i < 10 for i in range(n)])),
+                       ('id == 4001', np.arange(n) == 4001)]:
+        for nq in (1, 3):
+            hits = c.search("f", data=Q[:nq], limit=7, filter=expr, output_fields=["speaker"])
+            rows_allowed = np.nonzero(keep)[0]
+            exp_ids, exp_d, _ = fs.search(V[rows_allowed], rows_allowed.astype(np.int64), Q[:nq], 7, "COSINE")
+            for qi in range(nq):
+                got = [h["id"] for h in hits[qi]]
+                want = [int(x) for x in exp_ids[qi] if x >= 0]
+                assert got == want, (expr, qi, got, want)
+                assert np.allclose([h["distance"] for h in hits[qi]], exp_d[qi][: len(want)], rtol=RTOL, atol=1e-6)
+    assert c.search("f", data=Q[:1], limit=3, filter='speaker == "nobody"') == [[]]
+    assert [e["id"] for e in c.query("f", filter="id in [3, 1, 2]", output_fields=["speaker"])] == [1, 2, 3]
+    with pytest.raises(pkg.MilvusException):
+        c.search("f", data=Q[:1], limit=3, filter='__import__("os")')
+    # the filter does not leak into the next, unfiltered search
+    plain = c.search("f", data=Q[:1], limit=3)[0]
+    assert [h["id"] for h in plain] == fs.search(V, np.arange(n), Q[:1], 3, "COSINE")[0][0].tolist()
+    c.close()
