@@ -287,14 +287,12 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // compare against the threshold; only a qualifying chunk builds the bit mask of its survivors.
             auto process = [&](const uint32_t (&v)[32], int col0) {
                 if (lv.dense) {
+                    const uint32_t allow = filt ? filt[(row0 + col0) >> 5] : ~0u;   // the chunk's 32 rows = one bitmap word
                     u64* dst = my_cand + (size_t)m * BLOCK_N + half * 128 + col0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                    {
-                        const uint32_t row = (uint32_t)(row0 + col0 + i);
-                        const bool keep = col0 + i < valid_cols && tau_k != ~0ull && (!filt || ((filt[row >> 5] >> (row & 31)) & 1u));
-                        dst[i] = keep ? avs_make_key(__uint_as_float(v[i]), row) : 0ull;
-                    }
+                        dst[i] = (col0 + i < valid_cols && tau_k != ~0ull && ((allow >> i) & 1u))
+                                     ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
                     return;
                 }
                 float gm[4];
@@ -320,6 +318,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         const int vc = valid_cols - col0;
                         mask = vc >= 32 ? mask : (vc <= 0 ? 0u : (mask & ((1u << vc) - 1)));
                     }
+                    if (filt) mask &= filt[(row0 + col0) >> 5];      // row filter: the chunk's 32 rows = one bitmap word
                     while (mask) {                     // more than STASH survivors (duplicate-heavy data): drain in rounds
                         uint32_t sub = mask;
                         if (n_stash + __popc(mask) > STASH) {
@@ -335,11 +334,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     if ((sub >> (8 * gi + i)) & 1) {
-                                        const uint32_t row = (uint32_t)(row0 + col0 + 8 * gi + i);
-                                        if (!filt || ((filt[row >> 5] >> (row & 31)) & 1u)) {
-                                            my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), row);
-                                            ++n_stash;
-                                        }
+                                        my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), (uint32_t)(row0 + col0 + 8 * gi + i));
+                                        ++n_stash;
                                     }
                                 }
                             }
