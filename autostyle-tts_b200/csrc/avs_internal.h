@@ -134,7 +134,10 @@ struct avs_store {
     int64_t filter_allowed = 0;       // number of set bits
     size_t filter_words = 0;          // allocated words
     float* gstat = nullptr;           // [4] device scalars: r_max, xnorm_max (non-negative, atomicMax on bits)
-    unsigned long long* dstat = nullptr;  // [8] device counters: repaired, uncertified
+    unsigned long long* dstat = nullptr;  // [8] device counters: repaired, uncertified, wide-rescored
+    unsigned long long* h_stats = nullptr;  // pinned host mirror of dstat, refreshed asynchronously after every search
+    unsigned long long seen_repaired = 0;
+    bool eps_rule = false;            // set once an exact repair was needed: the last threshold then honours eps
     AvsScratch sc;
     int num_sms = 148;
     // options
@@ -153,6 +156,8 @@ struct avs_store {
     void* nccl_comm = nullptr;
     void* p2p_state = nullptr;       // peer-memory exchange regions (comm.cu)
     int opt_p2p = 1;
+    int opt_final_sigma = 2;         // expected survivors of the last level = K' + sigma * sqrt(K' * ratio)
+    int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;
 };
 

@@ -156,6 +156,7 @@ __device__ __forceinline__ void warp_sort_desc(u64 (&k)[EPL], int lane) {
 struct SelectArgs {
     u64* cand; int* cnt; int cap; u64* tau; int j_rank; int is_final; int kprime; int64_t n_rows;
     u64* topkeys; int* topn; float* bound; int* status; int dense_total; int nq;
+    const float* eps; int k_eps;   // k_eps > 0 on the level that sets the LAST threshold: keep it 2.5 eps under the k-th score
 };
 
 // Shared tail of both select paths: `at(e)` returns the e-th best key (0 beyond n), `store(e, key)`
@@ -346,15 +347,36 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     int jj = a.j_rank;
     if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
     if (!a.is_final) {
-        const int keep = n >= jj ? jj : n;
+        int keep = n >= jj ? jj : n;
+        u64 tau_new = n >= jj ? sm[jj - 1] : a.tau[qq];
+        // Last threshold: besides leaving ~j*ratio survivors it must sit at least 2.5 eps below the k-th scan score
+        // seen so far, so that the rows it admits are enough for the wide-rescoring certificate
+        // (exact k-th >= scan k-th - eps  >  threshold + eps).  Large dims (big eps relative to the score spacing)
+        // get more survivors this way, small dims are unaffected.
+        if (a.k_eps > 0 && n >= a.k_eps && total <= a.cap) {
+            const u64 t_eps = avs_make_key(avs_key_score(sm[a.k_eps - 1]) - 2.5f * a.eps[qq], 0xFFFFFFFFu);
+            if (t_eps < tau_new) {
+                tau_new = t_eps;
+                int lo = keep, hi = n;                    // keys are sorted: first index with key < tau_new
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm[mid] >= tau_new) lo = mid + 1; else hi = mid; }
+                keep = lo;
+            }
+        }
         for (int i = threadIdx.x; i < keep; i += blockDim.x) c[i] = sm[i];
-    } else {
-        const int m = n < a.kprime ? n : a.kprime;
-        for (int i = threadIdx.x; i < a.kprime; i += blockDim.x) a.topkeys[(size_t)qq * a.kprime + i] = i < m ? sm[i] : 0ull;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) c[i] = sm[i];   // sorted: the wide rescoring stage reads it
-        if (threadIdx.x == 0) a.cnt[qq] = total;
+        if (threadIdx.x == 0) {
+            a.tau[qq] = tau_new;
+            a.cnt[qq] = keep;
+            if (total > a.cap) a.status[qq] |= ST_OVERFLOW;
+        }
+        return;
     }
-    if (threadIdx.x == 0) select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1]);
+    const int m = n < a.kprime ? n : a.kprime;
+    for (int i = threadIdx.x; i < a.kprime; i += blockDim.x) a.topkeys[(size_t)qq * a.kprime + i] = i < m ? sm[i] : 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c[i] = sm[i];   // sorted: the wide rescoring stage reads it
+    if (threadIdx.x == 0) {
+        a.cnt[qq] = total;
+        select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -797,7 +819,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
-        const int64_t r = (fine_levels && L <= 3) ? 4 : rho;
+        const int64_t r = (fine_levels && L <= 3) ? s->opt_fine_ratio : rho;
         strides[L] = strides[L - 1] * r;
         ++L;
     }
@@ -823,7 +845,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         double need = 0.0;
         for (int i = L - 2; i >= 0; --i) {
             const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
-            if (i == L - 2) need = (double)kprime + 8.0 * sqrt((double)kprime * ratio);
+            if (i == L - 2) need = (double)kprime + (fine_levels ? (double)s->opt_final_sigma : 8.0) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
             j_ranks[i] = (int)j;
@@ -836,6 +858,10 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     s->st_last_levels = L;
     s->st_last_path = use_gemm ? 2 : 1;
 
+    // Adaptive policy, no host synchronisation: the counters of earlier searches arrive in pinned memory whenever
+    // their copy executes.  Once a query needed the exact repair scan (large dims: eps is big against the score
+    // spacing), the last threshold is kept 2.5 eps under the k-th score so that wide rescoring suffices.
+    if (s->h_stats && s->h_stats[0] > s->seen_repaired) { s->seen_repaired = s->h_stats[0]; s->eps_rule = true; }
     AVS_CUDA(cudaMemsetAsync(c.flagged, 0, sizeof(int), st));
     AVS_CUDA(cudaMemsetAsync(c.flagged2, 0, sizeof(int), st));
     const int n_slots = use_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
@@ -865,7 +891,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         }
         if (timed) timing_end(s, st, slot);
         SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, n_eff, c.topkeys, c.topn,
-                         bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq};
+                         bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq,
+                         use_gemm ? c.eps_gemm : c.eps_gemv, (l == L - 2 && fine_levels && s->eps_rule) ? k : 0};
         select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
@@ -892,6 +919,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
+    if (s->h_stats) AVS_CUDA(cudaMemcpyAsync(s->h_stats, s->dstat, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     return AVS_OK;
 }
 
@@ -937,6 +965,8 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "force_repair") s->opt_force_repair = (int)value;
     else if (k == "cta_group") s->opt_cta_group = value == 2 ? 2 : 1;
     else if (k == "p2p_merge") s->opt_p2p = value != 0;
+    else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
+    else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else { avs_set_error("avs_set_option: unknown option '%s'", key); return AVS_E_INVALID; }
     return AVS_OK;
 }

@@ -258,6 +258,8 @@ extern "C" int avs_create(int device, int dim, int metric, int64_t capacity, avs
     }
     cudaMemset(s->gstat, 0, 4 * sizeof(float));
     cudaMemset(s->dstat, 0, 8 * sizeof(u64));
+    if (cudaHostAlloc((void**)&s->h_stats, 8 * sizeof(u64), cudaHostAllocDefault) == cudaSuccess) memset(s->h_stats, 0, 8 * sizeof(u64));
+    else { cudaGetLastError(); s->h_stats = nullptr; }
     *out = s;
     return AVS_OK;
 }
@@ -276,6 +278,7 @@ extern "C" int avs_destroy(avs_store* s) {
     cudaFree(s->gstat);
     cudaFree(s->filter);
     cudaFree(s->dstat);
+    if (s->h_stats) cudaFreeHost(s->h_stats);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     cudaGetLastError();
     delete s;
