@@ -819,7 +819,12 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
-        const int64_t r = (fine_levels && L <= 3) ? s->opt_fine_ratio : rho;
+        int64_t r = (fine_levels && L <= 3) ? s->opt_fine_ratio : rho;
+        if (r == rho) {   // last coarse step: no sparser than needed to bring the threshold-free level under its row cap
+            const int64_t g_prev = (G + strides[L - 1] - 1) / strides[L - 1];
+            const int64_t r_needed = (g_prev * AVS_GROUP_ROWS + level0_rows - 1) / level0_rows;
+            if (r_needed < r) r = r_needed < 2 ? 2 : r_needed;
+        }
         strides[L] = strides[L - 1] * r;
         ++L;
     }
