@@ -19,7 +19,9 @@ WANT = ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max.per_second",
         "derived__lts__lts2xbar_bytes.sum.per_second", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "sm__inst_executed_pipe_tensor", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum")
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_tensor", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed")
 
 
 def raw_metrics(rep):
