@@ -424,10 +424,10 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
     CUtensorMap mq, mx;
     AVS_CHECK(make_map(&mq, s->sc.qb, nq_pad, s->dpad, BLOCK_M));
     AVS_CHECK(make_map(&mx, s->xb, s->capacity, s->dpad, C::LOAD_N));
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};   // function attributes are per device
+    if (!attr[s->device & 63]) {
         AVS_CUDA(cudaFuncSetAttribute(scan_gemm_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr = true;
+        attr[s->device & 63] = true;
     }
     int64_t clusters = s->num_sms / CG;
     if (clusters > lv.n_visit * n_qblocks) clusters = lv.n_visit * n_qblocks;

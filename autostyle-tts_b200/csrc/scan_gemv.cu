@@ -132,10 +132,10 @@ template <int NQ>
 static int launch_gemv(avs_store* s, int q0, const AvsLevel& lv, int cap, cudaStream_t st) {
     const int ppr = s->dpad / 8;
     const size_t smem = (size_t)NQ * 2 * ppr * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // function attributes are per device
+    if (!attr_set[s->device & 63]) {
         AVS_CUDA(cudaFuncSetAttribute(scan_gemv_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[s->device & 63] = true;
     }
     if (smem > 200 * 1024) { avs_set_error("gemv scan: %d queries x %d dims do not fit shared memory", NQ, s->dpad); return AVS_E_INVALID; }
     const int64_t want = (lv.n_visit * (AVS_GROUP_ROWS / GEMV_ROWS) + GEMV_THREADS / 32 - 1) / (GEMV_THREADS / 32);

@@ -875,14 +875,14 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
 
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};   // function attributes are per device
+    if (!attr_done[s->device & 63]) {
         AVS_CUDA(cudaFuncSetAttribute(select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         AVS_CUDA(cudaFuncSetAttribute(repair_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(AVS_REPAIR_CAP * sizeof(Hit))));
         AVS_CUDA(cudaFuncSetAttribute(wide_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(AVS_WIDE_MAX * sizeof(Hit))));
-        attr_done = true;
+        attr_done[s->device & 63] = true;
     }
 
     for (int l = 0; l < L; ++l) {

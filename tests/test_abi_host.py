@@ -217,3 +217,16 @@ def test_hot_kernels_stay_lean_and_blackwell_native(pkg):
     assert any("UTCHMMA.2CTA" in f for f in gemm)
     for f in gemv:
         assert re.search(r"LDG\.E\.128", f), "gemv scan lost its 128-bit loads"
+
+
+def test_bench_reference_arm_runs_offline():
+    """`bench.py --impl reference` (the driver's reference arm) needs no GPU: CPU port of the FLAT search."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "3000", "--dim", "64",
+                          "--steps", "1", "--warmup", "1", "--batch", "16"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "queries/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
