@@ -4,7 +4,7 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this module; the product path
 (`autostyle-tts_b200/`) must never route through it.
 
-PARITY PINNING: the reference holds NO asserting test for this boundary
+PARITY PINNING — "parity unpinned" against the engine: the reference holds NO asserting test for this boundary
  and its engine (pymilvus -> milvus-lite, unpinned:
 `/root/reference/milvus/RAG.py:2`) is an un-vendored third-party dependency
 that cannot be installed here.  The oracle is therefore pinned against
@@ -16,8 +16,8 @@ convention and row schema of the reference's real output
 `/root/reference/output_emb/search_results.json` (cosine SIMILARITY, larger is
 better, 0.81-0.95), and (3) agreement of three independent arithmetic variants
 (f64, fp32 normalise-then-dot, fp32 dot-then-divide) on the top-5 lists.  With
-no runnable Milvus Lite the parity claim is "pinned to shipped artefacts,
-engine-unpinned" — see DESIGN.md.
+no runnable Milvus Lite the parity claim is "parity unpinned with respect to the
+engine; pinned to the reference's shipped artefacts and inline check" — see DESIGN.md.
 
 What is restated (reference call sites):
   * `client.search(collection_name, data=[vec], limit=k, output_fields=[...])`
