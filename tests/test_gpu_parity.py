@@ -425,12 +425,13 @@ def test_scalar_filter_expressions(pkg):
     c.create_collection("f", dimension=d)
     c.insert("f", [{"id": i, "vector": V[i], "speaker": speakers[i % 3], "dur": float(i % 17), "file_id": f"{speakers[i % 3]}_{i}.wav"}
                    for i in range(n)])
-    Q = V[[5, 77, 4001]] + 0.01 * rng.standard_normal((3, d)).astype(np.float32)
+    Q = V[rng.integers(0, n, size=40)] + 0.01 * rng.standard_normal((40, d)).astype(np.float32)
+    Q[:3] = V[[5, 77, 4001]] + 0.01 * rng.standard_normal((3, d)).astype(np.float32)
     for expr, keep in [('speaker == "emma"', np.arange(n) % 3 == 0),
                        ('speaker in ["conan", "tonight"] and dur >= 5', (np.arange(n) % 3 != 0) & (np.arange(n) % 17 >= 5)),
                        ('file_id like "tonight_4%" || id < 10', np.array([(i % 3 == 2 and str(i).startswith("4")) or i < 10 for i in range(n)])),
                        ('id == 4001', np.arange(n) == 4001)]:
-        for nq in (1, 3):
+        for nq in (1, 3, 40):                               # gemv scan, and the tensor-core scan (bitmap word per chunk)
             hits = c.search("f", data=Q[:nq], limit=7, filter=expr, output_fields=["speaker"])
             rows_allowed = np.nonzero(keep)[0]
             exp_ids, exp_d, _ = fs.search(V[rows_allowed], rows_allowed.astype(np.int64), Q[:nq], 7, "COSINE")
@@ -447,3 +448,19 @@ def test_scalar_filter_expressions(pkg):
     plain = c.search("f", data=Q[:1], limit=3)[0]
     assert [h["id"] for h in plain] == fs.search(V, np.arange(n), Q[:1], 3, "COSINE")[0][0].tolist()
     c.close()
+
+
+def test_many_queries_uncached_thresholds(pkg):
+    """More query slots than the tensor-core kernel caches in shared memory (2048): thresholds come from global."""
+    n, d, nq, k = 30_000, 64, 2500, 10
+    X, ids, Q = _data(n, d, nq, seed=31, scale=False)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        got_ids, got_d = st.search(Q, k)
+        assert st.stat("last_scan_path") == 2
+        exp_ids, exp_d, _ = fs.search_large(X, ids, Q, k, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
