@@ -47,11 +47,12 @@ def synth_rows(seed: int, first_row: int, n: int, dim: int) -> np.ndarray:
 
 
 def planted_queries(seed_q: int, seed_db: int, n_db: int, nq: int, dim: int, planted_frac: float = 0.1,
-                    noise: float = 0.1, seed_pick: int = 44) -> np.ndarray:
+                    noise: float = 0.1, seed_pick: int = 44, return_planted: bool = False):
     """Query set of SURVEY.md section 8d: stream `seed_q` rows, with a `planted_frac` share replaced by
     normalize(x_j + noise * g) for random database rows j (so true neighbours exist)."""
     q = synth_rows(seed_q, 0, nq, dim)
     n_pl = int(round(nq * planted_frac))
+    slots = rows = np.zeros(0, dtype=np.int64)
     if n_pl and n_db:
         rng = np.random.default_rng(seed_pick)
         slots = rng.choice(nq, size=n_pl, replace=False)
@@ -60,4 +61,6 @@ def planted_queries(seed_q: int, seed_db: int, n_db: int, nq: int, dim: int, pla
         for s, r, gi in zip(slots, rows, g):
             x = synth_rows(seed_db, int(r), 1, dim)[0].astype(np.float64) + noise * gi.astype(np.float64)
             q[s] = (x / np.linalg.norm(x)).astype(np.float32)
+    if return_planted:
+        return q, np.asarray(slots, dtype=np.int64), np.asarray(rows, dtype=np.int64)
     return q

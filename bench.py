@@ -261,7 +261,7 @@ def run_ours(a):
     rows_local = len(st)
     dpad = (a.dim + 63) // 64 * 64
 
-    Qh = synth.planted_queries(SEED_Q, SEED_DB, a.rows, max(a.batch, 1), a.dim)
+    Qh, pl_slots, pl_rows = synth.planted_queries(SEED_Q, SEED_DB, a.rows, max(a.batch, 1), a.dim, return_planted=True)
     q_pinned = torch.from_numpy(Qh).pin_memory()
     q_dev = q_pinned.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -350,6 +350,12 @@ def run_ours(a):
                    "api": "avs_search_sharded (pinned H2D, D2H of ids+scores)"}
         results[batch] = {"dev_window": dev_window, "qps": batch / (ms * 1e-3), "ms": ms, "launches": int(launches), "roofline": roof, "e2e": e2e,
                           "scan_path": path, "levels": levels, "kprime": st.stat("last_kprime")}
+    # size-independent parity property at any scale: a query planted next to database row j must retrieve id j first
+    planted_ok = None
+    if pl_slots.size:
+        p_ids, _ = ss.search(q_dev[:a.batch], a.k)
+        p_ids = p_ids.cpu().numpy()
+        planted_ok = float(np.mean(p_ids[pl_slots, 0] == pl_rows))
     unc = st.stat("uncertified_queries")
     rep = st.stat("repaired_queries")
     wide = st.stat("wide_rescored_queries")
@@ -393,7 +399,7 @@ def run_ours(a):
                            "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],
                            "oversample_kprime": main["kprime"]},
                 "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
-                "cpu_baseline": cpu, "uncertified_queries": unc, "repaired_queries": rep,
+                "cpu_baseline": cpu, "planted_top1_match": planted_ok, "uncertified_queries": unc, "repaired_queries": rep,
                 "wide_rescored_queries": wide}
         if 1 in results and a.batch != 1:
             b1 = results[1]
