@@ -6,12 +6,16 @@
 //   D     = fp32 accumulators in TMEM: lane = query, column = database row, 2 x 256 columns
 //           (double buffered: the MMA of tile t+1 overlaps the epilogue of tile t)
 //   roles = warp 0 TMA producer | warp 1 tcgen05.mma issuer (one elected thread, leader CTA)
-//           | warp 2 TMEM allocator | warps 4-7 epilogue
-//   epilogue: thread t owns query lane t.  tcgen05.ld 32 columns -> max tree -> one compare with the
-//           query's running threshold held in a register; only survivors build a 64-bit key and
-//           are appended to the query's candidate buffer (global atomics, rare).
-// Work split: CTA (pair) c visits row groups c, c+C, ... of the level and sweeps ALL query blocks
-// over each group, so a database tile is read from HBM once and re-used from L2.
+//           | warp 2 TMEM allocator | warps 4-11 epilogue (two warps per TMEM lane quarter)
+//   epilogue: thread = (query lane, column half).  tcgen05.ld.32x32b.x32 (double buffered) -> 4 group
+//           maxima -> ONE compare with the query's threshold (cached in smem); a qualifying chunk builds
+//           the bit mask of its survivors (row filter = one bitmap word per chunk), stashes their 64-bit
+//           keys in shared memory, and reserves their slots in the query's candidate buffer with one
+//           atomicAdd per thread-tile whose result is only consumed a tile later.
+//           The threshold-free (sparsest) level stores every score densely instead, no atomics.
+// Work split: unit = (visited row group, query block of 128*CG queries); units are dealt round-robin to
+// the CTAs (pairs), so the pairs that run side by side sweep the query blocks over the same database
+// tile: one HBM read, the rest from L2.
 // Algorithmic flops per launch: 2 * nq_pad * rows_visited * D_pad.
 #include <cuda.h>
 

@@ -2,8 +2,8 @@
 // top-k selection fused into the epilogue: no score matrix is written, a row is appended to the
 // per-query candidate buffer only when its key beats the running threshold key.
 //
-// Layout: each warp owns 32 consecutive rows of a 256-row group and walks them 4 rows at a time.
-// A row is D_pad bf16 = D_pad/8 16-byte packets; lane l loads packets l, l+32, ... with
+// Layout: work unit = 4 consecutive rows; the units of the level's row groups are dealt round-robin to
+// all warps of the grid, so neighbouring warps stream neighbouring packets.  A row is D_pad bf16 = D_pad/8 16-byte packets; lane l loads packets l, l+32, ... with
 // ld.global.nc.L1::no_allocate.v4 (every warp-level load covers 512 contiguous bytes).  Queries
 // stay in shared memory as fp32 (not rounded to bf16, which halves the certificate slack), split
 // into two float4 planes so that the per-packet reads are bank-conflict free.

@@ -1,6 +1,6 @@
 // Search pipeline around the scan kernels:
-//   prep_queries  -> [scan level l -> select level l]* -> rescore_f64 -> finalize (+certificate)
-//   -> repair_scan / repair_finalize (device-gated: exit at once unless a query was flagged)
+//   prep_queries -> [scan level l -> select level l]* -> finalize (float64 rescoring of K' + certificate)
+//   -> wide_rescore -> repair_scan / repair_finalize (device-gated: exit at once unless a query was flagged)
 // Replaces the arithmetic behind `MilvusClient.search`
 // (/root/reference/milvus/search_embeddings.py:15-22, /root/reference/milvus/RAG.py:383-390).
 #include <math.h>
