@@ -170,3 +170,4 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
 int avs_scratch_reserve(avs_store* s, int nq, int kprime, int cap, int k);
 void avs_scratch_free(avs_store* s);
 void avs_comm_free(avs_store* s);
+int avs_p2p_timeouts(avs_store* s, int64_t* out);

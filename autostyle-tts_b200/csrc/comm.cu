@@ -214,6 +214,17 @@ static void p2p_free(avs_store* s) {
     s->p2p_state = nullptr;
 }
 
+// number of bounded spins that gave up waiting for a peer (0 in a healthy job); read by avs_get_stat("p2p_timeouts")
+int avs_p2p_timeouts(avs_store* s, int64_t* out) {
+    P2PState* st = (P2PState*)s->p2p_state;
+    *out = 0;
+    if (!st || !st->local) return AVS_OK;
+    unsigned int v = 0;
+    AVS_CUDA(cudaMemcpy(&v, &st->local->timeouts, sizeof(v), cudaMemcpyDeviceToHost));
+    *out = (int64_t)v;
+    return AVS_OK;
+}
+
 extern "C" int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out) {
     if (!s || !handle64_out || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) { avs_set_error("avs_p2p_init: bad arguments (rank %d, world %d, max world %d)", rank, world, P2P_MAX_WORLD); return AVS_E_INVALID; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");

@@ -985,6 +985,7 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "last_kprime") *out = s->st_last_kprime;
     else if (k == "last_levels") *out = s->st_last_levels;
     else if (k == "last_final_rows") *out = s->st_last_final_rows;
+    else if (k == "p2p_timeouts") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_timeouts(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries") {
         AVS_CUDA(cudaSetDevice(s->device));

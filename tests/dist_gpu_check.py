@@ -52,7 +52,7 @@ def main():
         if rank == 0:
             print(f"world={world} n={n} d={d} nq={nq} k={k} {metric}: {'OK' if flag.item() else 'MISMATCH'} "
                   f"(modes {[m[0] for m in modes]}, shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
-                  f"uncertified {ss.store.stat('uncertified_queries')})", flush=True)
+                  f"uncertified {ss.store.stat('uncertified_queries')}, p2p timeouts {ss.store.stat('p2p_timeouts')})", flush=True)
         ok &= bool(flag.item())
         ss.close()
     dist.destroy_process_group()
