@@ -48,6 +48,7 @@ class _Collection:
         self.meta: List[Dict[str, Any]] = []   # scalar + dynamic fields per row (no vector)
         self.next_auto = 1
         self.pending: List[np.ndarray] = []    # vectors loaded from disk, not yet on the device
+        self.filter_cache: Dict[str, np.ndarray] = {}   # expression -> row mask, valid until the next insert
 
     @property
     def scalar_field_names(self) -> List[str]:
@@ -263,6 +264,7 @@ class MilvusClient:
             raise MilvusException(e.message, e.code) from e
         coll.pks.extend(pks)
         coll.meta.extend(metas)
+        coll.filter_cache.clear()
         if coll.auto_id:
             coll.next_auto += len(data)
         if self._file is not None:
@@ -400,12 +402,18 @@ class MilvusClient:
             return None
         if not isinstance(expr, str):
             raise MilvusException(f"wrong type of argument 'filter', expected 'str', got '{type(expr).__name__}'")
+        cached = coll.filter_cache.get(expr)
+        if cached is not None and cached.shape[0] == len(coll.pks):
+            return cached
         pred = compile_filter(expr)
         mask = np.zeros(len(coll.pks), dtype=bool)
         for r, pk in enumerate(coll.pks):
             fields = dict(coll.meta[r])
             fields[coll.pk_name] = pk
             mask[r] = pred(fields)
+        if len(coll.filter_cache) >= 16:
+            coll.filter_cache.pop(next(iter(coll.filter_cache)))
+        coll.filter_cache[expr] = mask
         return mask
 
     def _coll(self, name: str) -> _Collection:
