@@ -236,6 +236,8 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    if not os.path.exists(os.path.join(ROOT, "autostyle-tts_b200", "libavs.so")) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        importlib.import_module("autostyle-tts_b200.build").build()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

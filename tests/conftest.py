@@ -14,6 +14,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the C-ABI library is a build artefact (git-ignored): compile it if this checkout does not have it yet
+    lib = os.path.join(ROOT, "autostyle-tts_b200", "libavs.so")
+    if not os.path.exists(lib):
+        try:
+            importlib.import_module("autostyle-tts_b200.build").build()
+        except Exception as e:  # the tests that need it will fail loudly with the reason
+            print(f"[conftest] could not build libavs.so: {e}")
 
 
 def load_pkg(sub: str = ""):
