@@ -110,10 +110,10 @@ struct AvsScratch {
     void* gather_send = nullptr;  // [nq, k] (f64 score, i64 id)
     void* gather_recv = nullptr;  // [world, nq, k]
     // host staging for avs_search_host
-    float* h2d_q = nullptr;
-    int64_t* d_ids = nullptr;
-    float* d_scores = nullptr;
-    int64_t* d_rows = nullptr;
+    float* h2d_q = nullptr;       // device copy of the host queries
+    int64_t* d_ids = nullptr;     // device result block [ids | rows | scores]
+    int64_t* h_out = nullptr;     // pinned mirror of the result block
+    float* h_q = nullptr;         // pinned stage for pageable host queries
     // sizes the buffers were allocated for
     size_t gather_items = 0;
     int nq_cap = 0, kprime_cap = 0, cap_cap = 0, k_cap = 0, world_cap = 0, host_nq_cap = 0, host_k_cap = 0;

@@ -688,8 +688,10 @@ void avs_scratch_free(avs_store* s) {
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
     cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.rep_s); cudaFree(c.rep_row);
     cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
-    cudaFree(c.d_ids); cudaFree(c.d_scores); cudaFree(c.d_rows);
+    cudaFree(c.d_ids);
     if (c.h2d_q) cudaFree(c.h2d_q);
+    if (c.h_out) cudaFreeHost(c.h_out);
+    if (c.h_q) cudaFreeHost(c.h_q);
     c = AvsScratch();
 }
 
@@ -941,22 +943,43 @@ extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k,
     if (nq == 0) return AVS_OK;
     AVS_CUDA(cudaSetDevice(s->device));
     AvsScratch& c = s->sc;
+    // one device block [ids | rows | scores] and one pinned host mirror: a single D2H copy brings every result back
+    const size_t items = (size_t)nq * k;
     if (nq > c.host_nq_cap || k > c.host_k_cap) {
         AVS_CUDA(cudaDeviceSynchronize());
         const int nq2 = nq > c.host_nq_cap ? nq : c.host_nq_cap, k2 = k > c.host_k_cap ? k : c.host_k_cap;
+        const size_t cap_items = (size_t)nq2 * k2;
         AVS_CHECK(dev_alloc(&c.h2d_q, (size_t)nq2 * s->dim));
-        AVS_CHECK(dev_alloc(&c.d_ids, (size_t)nq2 * k2));
-        AVS_CHECK(dev_alloc(&c.d_scores, (size_t)nq2 * k2));
-        AVS_CHECK(dev_alloc(&c.d_rows, (size_t)nq2 * k2));
+        AVS_CHECK(dev_alloc(&c.d_ids, cap_items * 3));                 // ids, rows (int64) and scores (fp32, 8-byte slots)
+        if (c.h_out) cudaFreeHost(c.h_out);
+        if (c.h_q) cudaFreeHost(c.h_q);
+        c.h_out = nullptr; c.h_q = nullptr;
+        if (cudaHostAlloc((void**)&c.h_out, cap_items * 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&c.h_q, (size_t)nq2 * s->dim * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            avs_set_error("out of pinned host memory for the search staging buffers");
+            return AVS_E_NOMEM;
+        }
         c.host_nq_cap = nq2; c.host_k_cap = k2;
     }
+    int64_t* d_ids = c.d_ids;
+    int64_t* d_rows = c.d_ids + items;
+    float* d_scores = reinterpret_cast<float*>(c.d_ids + 2 * items);
     cudaStream_t st = 0;
-    AVS_CUDA(cudaMemcpyAsync(c.h2d_q, q_host, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-    AVS_CHECK(avs_search_local(s, c.h2d_q, nq, k, c.d_ids, c.d_scores, c.d_rows, st));
-    AVS_CUDA(cudaMemcpyAsync(out_ids_host, c.d_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    AVS_CUDA(cudaMemcpyAsync(out_scores_host, c.d_scores, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out_rows_host) AVS_CUDA(cudaMemcpyAsync(out_rows_host, c.d_rows, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    // queries: from the caller's buffer directly when it is already pinned (no extra host copy), else via the pinned stage
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, q_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const float* src = q_host;
+    if (!pinned) { memcpy(c.h_q, q_host, (size_t)nq * s->dim * sizeof(float)); src = c.h_q; }
+    AVS_CUDA(cudaMemcpyAsync(c.h2d_q, src, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    AVS_CHECK(avs_search_local(s, c.h2d_q, nq, k, d_ids, d_scores, d_rows, st));
+    const size_t out_bytes = items * (2 * sizeof(int64_t) + sizeof(float));
+    AVS_CUDA(cudaMemcpyAsync(c.h_out, c.d_ids, out_bytes, cudaMemcpyDeviceToHost, st));
     AVS_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_ids_host, c.h_out, items * sizeof(int64_t));
+    if (out_rows_host) memcpy(out_rows_host, c.h_out + items, items * sizeof(int64_t));
+    memcpy(out_scores_host, c.h_out + 2 * items, items * sizeof(float));
     return AVS_OK;
 }
 
