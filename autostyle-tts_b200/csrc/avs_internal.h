@@ -18,6 +18,8 @@ typedef unsigned long long u64;
 #define AVS_REPAIR_CAP 4096     // exact-repair collection buffer per flagged query
 #define AVS_MAX_REPAIR_Q 256    // flagged queries repaired per search
 #define AVS_MAX_LEVELS 12
+#define AVS_DENSE_CAP 65536      // rows of the threshold-free level of the gemv path (dense key buffer per query)
+#define AVS_DENSE_MAX_NQ 64      // the dense buffer is kept for this many queries
 
 // ---- error plumbing -------------------------------------------------------------------------
 void avs_set_error(const char* fmt, ...);
@@ -95,6 +97,7 @@ struct AvsScratch {
     u64* cand = nullptr;          // [nq, cap]
     int* cnt = nullptr;           // [nq]
     u64* tau = nullptr;           // [nq_pad] running threshold key
+    u64* dense_buf = nullptr;     // [AVS_DENSE_MAX_NQ + 8, AVS_DENSE_CAP] keys of the gemv path's threshold-free level
     u64* topkeys = nullptr;       // [nq, kprime] final bf16-scan candidates, sorted desc
     int* topn = nullptr;          // [nq]
     int* status = nullptr;        // [nq] bit0 overflow, bit1 underflow, bit2 cert failed, bit3 uncertified

@@ -63,7 +63,8 @@ template <int NQ>
 __global__ void __launch_bounds__(GEMV_THREADS, 2)
 scan_gemv_kernel(const uint4* __restrict__ xb, int packets_per_row, int64_t n_rows,
                  const float* __restrict__ qf, int dpad, const u64* __restrict__ tau, AvsLevel lv,
-                 u64* __restrict__ cand, int* __restrict__ cnt, int cap, const uint32_t* __restrict__ filt) {
+                 u64* __restrict__ cand, int* __restrict__ cnt, int cap, const uint32_t* __restrict__ filt,
+                 u64* __restrict__ dense, int dense_cap) {
     extern __shared__ float4 sq[];  // [NQ][2][packets_per_row]: plane 0 = first 4 floats of a packet
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -117,7 +118,14 @@ scan_gemv_kernel(const uint4* __restrict__ xb, int packets_per_row, int64_t n_ro
             const bool owner = (DUP <= 1) || ((lane & (DUP - 1)) == 0);
             const int r = idx / NQ, q = idx - r * NQ;
             const int64_t row = rbase + r;
-            if (owner && row < n_rows && s >= tau_f[q] && (!filt || ((filt[row >> 5] >> (row & 31)) & 1u))) {
+            if (lv.dense) {
+                // threshold-free level: every visited row's key goes to its own slot (0 = padding / filtered out)
+                if (owner) {
+                    const bool keep = row < n_rows && (!filt || ((filt[row >> 5] >> (row & 31)) & 1u));
+                    const int64_t slot = m * AVS_GROUP_ROWS + (u - m * UNITS) * GEMV_ROWS + r;
+                    dense[(size_t)q * dense_cap + slot] = keep ? avs_make_key(s, (uint32_t)row) : 0ull;
+                }
+            } else if (owner && row < n_rows && s >= tau_f[q] && (!filt || ((filt[row >> 5] >> (row & 31)) & 1u))) {
                 const u64 key = avs_make_key(s, (uint32_t)row);
                 if (key >= tau_k[q]) {
                     const int pos = atomicAdd(cnt + q, 1);
@@ -143,7 +151,8 @@ static int launch_gemv(avs_store* s, int q0, const AvsLevel& lv, int cap, cudaSt
     if (grid < 1) grid = 1;
     scan_gemv_kernel<NQ><<<(unsigned)grid, GEMV_THREADS, smem, st>>>(
         reinterpret_cast<const uint4*>(s->xb), ppr, s->count, s->sc.qf + (size_t)q0 * s->dpad, s->dpad,
-        s->sc.tau + q0, lv, s->sc.cand + (size_t)q0 * cap, s->sc.cnt + q0, cap, s->filter);
+        s->sc.tau + q0, lv, s->sc.cand + (size_t)q0 * cap, s->sc.cnt + q0, cap, s->filter,
+        s->sc.dense_buf ? s->sc.dense_buf + (size_t)q0 * AVS_DENSE_CAP : nullptr, AVS_DENSE_CAP);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     return AVS_OK;

@@ -156,6 +156,7 @@ __device__ __forceinline__ void warp_sort_desc(u64 (&k)[EPL], int lane) {
 struct SelectArgs {
     u64* cand; int* cnt; int cap; u64* tau; int j_rank; int is_final; int kprime; int64_t n_rows;
     u64* topkeys; int* topn; float* bound; int* status; int dense_total; int nq;
+    const u64* dense_src; int dense_stride;   // gemv path: the threshold-free level's keys live in their own buffer
     const float* eps; int k_eps;   // k_eps > 0 on the level that sets the LAST threshold: keep it 2.5 eps under the k-th score
 };
 
@@ -189,21 +190,22 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int qq = blockIdx.x;
     int total = a.dense_total > 0 ? a.dense_total : a.cnt[qq];
-    int n = total < a.cap ? total : a.cap;
+    int n = (total < a.cap || a.dense_src) ? total : a.cap;
     int P = 32;
     while (P < n) P <<= 1;
-    u64* c = a.cand + (size_t)qq * a.cap;
+    u64* c = a.cand + (size_t)qq * a.cap;                                        // survivors are written here
+    const u64* cin = a.dense_src ? a.dense_src + (size_t)qq * a.dense_stride : c;   // keys are read from here
     // Intermediate level with many keys and a small rank j (the dense sparsest level: 1024-2048 keys, j ~ 16):
     // no full sort.  The j-th largest of 64 strided group maxima is a lower bound P of the j-th largest key, the
     // keys >= P (j..a few dozen) are compacted and sorted by one warp in registers.
-    if (!a.is_final && total <= a.cap && a.j_rank <= 32 && n >= 32 * a.j_rank) {
+    if (!a.is_final && (total <= a.cap || a.dense_src) && a.j_rank <= 32 && n >= 32 * a.j_rank) {
         __shared__ u64 gmax64[64];
         __shared__ u64 lst[256];
         __shared__ int s_m;
         __shared__ u64 s_P;
         const int nt = blockDim.x, tid = threadIdx.x;
         u64 lm = 0;
-        for (int i = tid; i < n; i += nt) { const u64 key = c[i]; lm = key > lm ? key : lm; }
+        for (int i = tid; i < n; i += nt) { const u64 key = cin[i]; lm = key > lm ? key : lm; }
         sm[tid] = lm;
         if (tid == 0) s_m = 0;
         __syncthreads();
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         const u64 P = s_P;
         if (P != 0ull) {
             for (int i = tid; i < n; i += nt) {
-                const u64 key = c[i];
+                const u64 key = cin[i];
                 if (key >= P) { const int pos = atomicAdd(&s_m, 1); if (pos < 256) lst[pos] = key; }
             }
         }
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     // Large collected sets (big K', many-row dense level): 8-pass byte-wise radix select of the rank-`want` key
     // straight from L2 (O(n) per pass, no 64-128 KB of shared memory) and an unordered compaction of the keys
     // above it.  Neither the next level nor the rescoring stage needs the survivors sorted.
-    if (n > 1024) {
+    if (n > 1024 || a.dense_src) {
         __shared__ int hist[256];
         __shared__ int s_sel[2];
         __shared__ u64 lst[256];
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
             if (tid == 0) s_m = 0;
             __syncthreads();
             int nzc = 0;
-            for (int i = tid; i < n; i += nt) nzc += c[i] != 0ull;
+            for (int i = tid; i < n; i += nt) nzc += cin[i] != 0ull;
 #pragma unroll
             for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
             if (lane == 0 && nzc) atomicAdd(&s_m, nzc);
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
                 __syncthreads();
                 for (int i0 = 0; i0 < n; i0 += nt) {      // whole warps stay converged for the match below
                     const int i = i0 + tid;
-                    const u64 key = i < n ? c[i] : 0ull;
+                    const u64 key = i < n ? cin[i] : 0ull;
                     const bool in = i < n && (key & maskb) == prefix;
                     const int bin = in ? (int)((key >> (8 * byte)) & 0xFFull) : 256 + lane;   // non-members: unique dummies
                     // scores share their leading bytes: aggregate equal bins inside the warp, one atomic per bin
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         if (a.is_final) for (int i = tid; i < a.kprime; i += nt) a.topkeys[(size_t)qq * a.kprime + i] = 0ull;
         __syncthreads();
         for (int i = tid; i < n; i += nt) {
-            const u64 key = c[i];
+            const u64 key = cin[i];
             if (key >= Pk && key != 0ull) {
                 const int pos = atomicAdd(&s_m, 1);
                 if (a.is_final) { if (pos < a.kprime) a.topkeys[(size_t)qq * a.kprime + pos] = key; }
@@ -324,7 +326,21 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         __syncthreads();
         if (!a.is_final) {
             for (int i = tid; i < want && i < 256; i += nt) c[i] = lst[i];
-        } else if (tid == 0) a.cnt[qq] = total;
+        } else if (a.dense_src) {
+            // single-level search on the gemv path: the keys live in the dense buffer; the wide-rescoring stage reads
+            // the candidate buffer, so hand it every real key when they fit (else it defers to the exact scan)
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            if (n_real <= a.cap) {
+                for (int i = tid; i < n; i += nt) {
+                    const u64 key = cin[i];
+                    if (key != 0ull) c[atomicAdd(&s_m, 1)] = key;
+                }
+            }
+            if (tid == 0) a.cnt[qq] = n_real <= a.cap ? n_real : a.cap + 1;
+        } else if (tid == 0) {
+            a.cnt[qq] = a.dense_total > 0 ? n : total;   // dense level inside the buffer: slots (zero = empty), not keys
+        }
         if (tid == 0) select_emit_scalar(a, qq, total, n_real, Pk, Pk);
         return;
     }
@@ -505,25 +521,32 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
     const int f = blockIdx.x;
     if (f >= nf) return;
     const int q = flagged[1 + f];
-    const int total = cnt[q];
-    // the buffer is not necessarily sorted: rescore all of it or hand the query to the exact scan
-    const bool lost = total > cap || total > AVS_WIDE_MAX || (status[q] & ST_OVERFLOW);
-    const int n = lost ? 0 : total;
+    const int slots = cnt[q];
+    // the buffer is not necessarily sorted and may hold empty (zero) slots: rescore all of it or hand the query on
+    const bool lost = slots > cap || slots > AVS_WIDE_MAX || (status[q] & ST_OVERFLOW);
+    const int ns = lost ? 0 : slots;
     const u64* c = cand + (size_t)q * cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
     int P = 32;
-    while (P < n) P <<= 1;
+    while (P < ns) P <<= 1;
     const double qn = qnorm[q];
     const float* qp = qraw + (size_t)q * dim;
     for (int i = warp; i < P; i += nwarps) {
         Hit h;
-        if (i < n && !lost) {
-            h.row = avs_key_row(c[i]);
+        const u64 key = i < ns ? c[i] : 0ull;
+        if (key != 0ull) {
+            h.row = avs_key_row(key);
             h.s = exact_score(master + (size_t)h.row * dim, qp, dim, qn, metric, lane);
             h.id = ids[h.row];
+            if (lane == 0) atomicAdd(&s_valid, 1);
         } else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
         if (lane == 0) sm[i] = h;
     }
+    __syncthreads();
+    const int n = s_valid, total = s_valid;
     __syncthreads();
     for (int k2 = 2; k2 <= P; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
@@ -686,7 +709,7 @@ void avs_scratch_free(avs_store* s) {
     AvsScratch& c = s->sc;
     cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
-    cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.rep_s); cudaFree(c.rep_row);
+    cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.dense_buf); cudaFree(c.rep_s); cudaFree(c.rep_row);
     cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
     cudaFree(c.d_ids);
     if (c.h2d_q) cudaFree(c.h2d_q);
@@ -724,6 +747,7 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
     if (grow_q || grow_k) AVS_CHECK(dev_alloc(&c.out_s64, (size_t)nq2 * k2));
     if (!c.flagged2) {
         AVS_CHECK(dev_alloc(&c.flagged2, (size_t)1 + AVS_MAX_REPAIR_Q));
+        AVS_CHECK(dev_alloc(&c.dense_buf, (size_t)(AVS_DENSE_MAX_NQ + 8) * AVS_DENSE_CAP));
         AVS_CHECK(dev_alloc(&c.rep_s, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
         AVS_CHECK(dev_alloc(&c.rep_row, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
         AVS_CHECK(dev_alloc(&c.rep_cnt, (size_t)AVS_MAX_REPAIR_Q));
@@ -817,7 +841,10 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     int64_t strides[AVS_MAX_LEVELS];
     int L = 1;
     strides[0] = 1;
-    const int64_t level0_rows = cap < 2048 ? cap : 2048;   // the threshold-free level stays small whatever K' is
+    // the threshold-free level: <= 2048 rows inside the candidate buffer on the tensor-core path; the gemv path (few
+    // queries) stores up to 64 K rows densely in its own buffer, which saves it a whole intermediate level
+    const bool dense_gemv = !use_gemm && nq <= AVS_DENSE_MAX_NQ;
+    const int64_t level0_rows = dense_gemv ? AVS_DENSE_CAP : (cap < 2048 ? cap : 2048);
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
@@ -839,7 +866,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         lv[i].skip = i == 0 ? 0 : strides[L - i];
         lv[i].ratio = i == 0 ? 0 : lv[i].skip / stride;
         lv[i].n_visit = lv[i].ratio > 1 ? lv[i].n_iter - (lv[i].n_iter + lv[i].ratio - 1) / lv[i].ratio : lv[i].n_iter;
-        lv[i].dense = (i == 0 && use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ? 1 : 0;
+        lv[i].dense = (i == 0 && ((use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ||
+                                  (dense_gemv && lv[i].n_iter * AVS_GROUP_ROWS <= AVS_DENSE_CAP))) ? 1 : 0;
         j_ranks[i] = 0;
     }
 
@@ -898,7 +926,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         }
         if (timed) timing_end(s, st, slot);
         SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, n_eff, c.topkeys, c.topn,
-                         bound, c.status, lv[l].dense ? (int)(lv[l].n_iter * AVS_GROUP_ROWS) : 0, nq,
+                         bound, c.status, lv[l].dense ? (int)(lv[l].n_visit * AVS_GROUP_ROWS) : 0, nq,
+                         (lv[l].dense && !use_gemm) ? c.dense_buf : nullptr, AVS_DENSE_CAP,
                          use_gemm ? c.eps_gemm : c.eps_gemv, (l == L - 2 && fine_levels && s->eps_rule) ? k : 0};
         select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
