@@ -457,7 +457,7 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
 }  // namespace
 
 int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
-    if (s->opt_cta_group == 1) return launch<1>(s, nq, lv, cap, st);
+    if (s->opt_cta_group == 1 || (nq <= BLOCK_M && s->opt_cta_group_small == 1)) return launch<1>(s, nq, lv, cap, st);
     return launch<2>(s, nq, lv, cap, st);
 }
 

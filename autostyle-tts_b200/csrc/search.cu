@@ -43,9 +43,11 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
                                                            float* __restrict__ qf, __nv_bfloat16* __restrict__ qb,
                                                            double* __restrict__ qnorm, float* __restrict__ eps_gemv,
                                                            float* __restrict__ eps_gemm, u64* __restrict__ tau,
-                                                           int* __restrict__ cnt, int* __restrict__ status) {
+                                                           int* __restrict__ cnt, int* __restrict__ status,
+                                                           int* __restrict__ flagged, int* __restrict__ flagged2) {
     __shared__ double sh[4];
     const int qi = blockIdx.x;
+    if (qi == 0 && threadIdx.x == 0) { flagged[0] = 0; flagged2[0] = 0; }   // repair queues of this search start empty
     float* of = qf + (size_t)qi * dpad;
     __nv_bfloat16* ob = qb + (size_t)qi * dpad;
     if (qi >= nq) {  // padding slot: zero vector, never accepts
@@ -396,18 +398,50 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact float64 score of one master row, one warp per (query, candidate).  Lane l accumulates
-// elements l, l+32, ... in order, then an xor-butterfly (commutative, so every lane ends with the
-// same bits).  The result depends only on the row's and the query's content: identical rows tie
-// exactly and fall through to the id comparison.  Used by both rescoring and repair.
+// Exact float64 score of one master row, one warp per (query, candidate).  Canonical accumulation order:
+// the row is cut into quads of 4 consecutive elements, lane l owns quads l, l+32, ... and accumulates them in
+// order (elements past `dim` count as zero), then an xor-butterfly (commutative, so every lane ends with the
+// same bits).  The result depends only on the row's and the query's content: identical rows tie exactly and
+// fall through to the id comparison.  16-byte aligned operands take the vector path (2 x 128-bit loads of the
+// row and of the query in flight per lane before the first FMA); the scalar path keeps the same order and
+// therefore the same bits.  Used by both rescoring and repair.
 // ---------------------------------------------------------------------------------------------
+#define AVS_XS_UNROLL 2
 __device__ __forceinline__ double exact_score(const float* __restrict__ x, const float* __restrict__ q, int dim,
                                               double qn, int metric, int lane) {
     double dot = 0.0, xx = 0.0;
-    for (int c = lane; c < dim; c += 32) {
-        const double a = (double)__ldg(x + c), b = (double)__ldg(q + c);
-        dot = fma(a, b, dot);
-        xx = fma(a, a, xx);
+    const int nquad = (dim + 3) >> 2;
+    const bool vec = ((dim & 3) == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q)) & 15) == 0);
+    if (vec) {
+        const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+        const float4* __restrict__ q4 = reinterpret_cast<const float4*>(q);
+        for (int base = 0; base < nquad; base += 32 * AVS_XS_UNROLL) {
+            float4 xv[AVS_XS_UNROLL], qv[AVS_XS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < AVS_XS_UNROLL; ++u) {
+                const int i = base + 32 * u + lane;
+                if (i < nquad) { xv[u] = __ldg(x4 + i); qv[u] = __ldg(q4 + i); }
+                else { xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); qv[u] = xv[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < AVS_XS_UNROLL; ++u) {
+                const double a0 = (double)xv[u].x, a1 = (double)xv[u].y, a2 = (double)xv[u].z, a3 = (double)xv[u].w;
+                dot = fma(a0, (double)qv[u].x, dot); xx = fma(a0, a0, xx);
+                dot = fma(a1, (double)qv[u].y, dot); xx = fma(a1, a1, xx);
+                dot = fma(a2, (double)qv[u].z, dot); xx = fma(a2, a2, xx);
+                dot = fma(a3, (double)qv[u].w, dot); xx = fma(a3, a3, xx);
+            }
+        }
+    } else {
+        for (int i = lane; i < nquad; i += 32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 4 * i + j;
+                const double a = e < dim ? (double)__ldg(x + e) : 0.0, b = e < dim ? (double)__ldg(q + e) : 0.0;
+                dot = fma(a, b, dot);
+                xx = fma(a, a, xx);
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -835,7 +869,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
     // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
     // last threshold is taken from a quarter of the database); the gemv path keeps fewer, coarser levels.
-    const bool fine_levels = use_gemm && nq >= 192;   // compute-bound regime only: extra levels cost launches
+    const bool fine_levels = use_gemm && nq >= s->opt_fine_min_batch;   // compute-bound regime only: extra levels cost launches
     const int64_t G = (s->count + AVS_GROUP_ROWS - 1) / AVS_GROUP_ROWS;
     const int64_t rho = s->opt_ratio < 2 ? 2 : s->opt_ratio;
     int64_t strides[AVS_MAX_LEVELS];
@@ -880,7 +914,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         double need = 0.0;
         for (int i = L - 2; i >= 0; --i) {
             const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
-            if (i == L - 2) need = (double)kprime + (fine_levels ? (double)s->opt_final_sigma : 8.0) * sqrt((double)kprime * ratio);
+            if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : s->opt_coarse_sigma) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
             j_ranks[i] = (int)j;
@@ -897,11 +931,9 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // their copy executes.  Once a query needed the exact repair scan (large dims: eps is big against the score
     // spacing), the last threshold is kept 2.5 eps under the k-th score so that wide rescoring suffices.
     if (s->h_stats && s->h_stats[0] > s->seen_repaired) { s->seen_repaired = s->h_stats[0]; s->eps_rule = true; }
-    AVS_CUDA(cudaMemsetAsync(c.flagged, 0, sizeof(int), st));
-    AVS_CUDA(cudaMemsetAsync(c.flagged2, 0, sizeof(int), st));
     const int n_slots = use_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
     prep_queries_kernel<<<n_slots, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
-                                                c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status);
+                                                c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status, c.flagged, c.flagged2);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
 
@@ -1024,6 +1056,9 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "p2p_merge") s->opt_p2p = value != 0;
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
+    else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;
+    else if (k == "coarse_sigma") s->opt_coarse_sigma = value < 1 ? 1 : (int)value;
+    else if (k == "cta_group_small") s->opt_cta_group_small = value == 1 ? 1 : 2;
     else { avs_set_error("avs_set_option: unknown option '%s'", key); return AVS_E_INVALID; }
     return AVS_OK;
 }

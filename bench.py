@@ -46,12 +46,14 @@ def parse():
     ap.add_argument("--scan-path", type=int, default=0, help="0 auto, 1 gemv, 2 gemm")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--only-batch", action="store_true", help="skip the extra batch-1 measurement")
+    ap.add_argument("--sweep", default="", help="comma-separated batch sizes measured on the same store; adds a `sweep` list to the JSON line")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather + merge instead of the fused peer-memory kernel")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return f"C2: {a.rows} x {a.dim} synthetic unit-norm rows, {a.metric} top-{a.k}, batch {a.batch} (and batch 1)"
+    tag = {(1_000_000, 768): "C2", (10_000_000, 1024): "C3", (12_500_000, 768): "C5 shard"}.get((a.rows, a.dim), "custom")
+    return f"{tag}: {a.rows} x {a.dim} synthetic unit-norm rows, {a.metric} top-{a.k}, batch {a.batch} (and batch 1)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,7 +265,8 @@ def run_ours(a):
     rows_local = len(st)
     dpad = (a.dim + 63) // 64 * 64
 
-    Qh, pl_slots, pl_rows = synth.planted_queries(SEED_Q, SEED_DB, a.rows, max(a.batch, 1), a.dim, return_planted=True)
+    sweep = sorted({int(b) for b in a.sweep.split(",") if b.strip()})
+    Qh, pl_slots, pl_rows = synth.planted_queries(SEED_Q, SEED_DB, a.rows, max([a.batch, 1] + sweep), a.dim, return_planted=True)
     q_pinned = torch.from_numpy(Qh).pin_memory()
     q_dev = q_pinned.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -297,7 +300,7 @@ def run_ours(a):
         clocks.start()
     windows = []
     results = {}
-    for batch in sorted({a.batch} if a.only_batch else {a.batch, 1}):   # small batch first: it is not the one that heats the chip
+    for batch in sorted(({a.batch} if a.only_batch else {a.batch, 1}) | set(sweep)):   # small batch first: it is not the one that heats the chip
         q = q_dev[:batch]
         qh = q_pinned[:batch].numpy()
         fn_dev = (lambda: ss.search(q, a.k))
@@ -355,7 +358,7 @@ def run_ours(a):
     # size-independent parity property at any scale: a query planted next to database row j must retrieve id j first
     planted_ok = None
     if pl_slots.size:
-        p_ids, _ = ss.search(q_dev[:a.batch], a.k)
+        p_ids, _ = ss.search(q_dev, a.k)
         p_ids = p_ids.cpu().numpy()
         planted_ok = float(np.mean(p_ids[pl_slots, 0] == pl_rows))
     unc = st.stat("uncertified_queries")
@@ -407,6 +410,13 @@ def run_ours(a):
             b1 = results[1]
             line["batch1"] = {"value": b1["qps"], "unit": "queries/s", "ms_per_step": b1["ms"], "e2e": b1["e2e"],
                               "gpu_launches": b1["launches"], "roofline": b1["roofline"]}
+        if sweep:
+            line["sweep"] = [{"batch": b, "value": results[b]["qps"], "ms_per_step": results[b]["ms"],
+                              "e2e": results[b]["e2e"]["value"] if results[b]["e2e"] else None,
+                              "scan_path": {1: "gemv", 2: "gemm"}.get(results[b]["scan_path"]), "levels": results[b]["levels"],
+                              "bound": results[b]["roofline"]["bound"], "achieved": results[b]["roofline"]["achieved"],
+                              "peak": results[b]["roofline"]["peak"], "frac": results[b]["roofline"]["frac"],
+                              "kernel_ms": results[b]["roofline"]["kernel_ms"]} for b in sweep]
         print(json.dumps(line), flush=True)
     ss.close()
     if world > 1:
