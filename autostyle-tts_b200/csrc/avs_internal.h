@@ -144,7 +144,7 @@ struct avs_store {
     AvsScratch sc;
     int num_sms = 148;
     // options
-    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 4, opt_ratio = 32, opt_force_repair = 0,
+    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 3, opt_ratio = 32, opt_force_repair = 0,
         opt_cta_group = 2;
     // stats
     int64_t st_launches = 0, st_searches = 0, st_queries = 0, st_last_final_rows = 0;
@@ -160,9 +160,9 @@ struct avs_store {
     void* p2p_state = nullptr;       // peer-memory exchange regions (comm.cu)
     int opt_p2p = 1;
     int opt_final_sigma = 2;         // expected survivors of the last level = K' + sigma * sqrt(K' * ratio)
-    int opt_fine_min_batch = 192;    // tensor-core path: batches from here on use the fine (x4) dense-end schedule
-    int opt_coarse_sigma = 8;        // same margin for the coarse (x32) schedules
-    int opt_cta_group_small = 2;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
+    int opt_fine_min_batch = 129;    // tensor-core path: batches from here on use the fine (x4) dense-end schedule
+    int opt_coarse_sigma = 3;        // same margin for the coarse (x32) schedule of the tensor-core path (gemv: 8)
+    int opt_cta_group_small = 1;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;
 };

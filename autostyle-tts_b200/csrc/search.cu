@@ -164,19 +164,20 @@ struct SelectArgs {
 
 // Shared tail of both select paths: `at(e)` returns the e-th best key (0 beyond n), `store(e, key)`
 // is only used by the block path.  Runs on one thread.
-__device__ __forceinline__ void select_emit_scalar(const SelectArgs& a, int q, int total, int n, u64 key_j, u64 key_kp) {
+// `lost`: more keys were offered than the buffer they were collected in can hold (never the case for the dense buffer).
+__device__ __forceinline__ void select_emit_scalar(const SelectArgs& a, int q, int total, int n, u64 key_j, u64 key_kp, bool lost) {
     if (!a.is_final) {
         int jj = a.j_rank;
-        if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
+        if (lost) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
         if (n >= jj) a.tau[q] = key_j;
         a.cnt[q] = n >= jj ? jj : n;
-        if (total > a.cap) a.status[q] |= ST_OVERFLOW;       // rows were lost for good: force the exact repair
+        if (lost) a.status[q] |= ST_OVERFLOW;                // rows were lost for good: force the exact repair
     } else {
         const int m = n < a.kprime ? n : a.kprime;
         a.topn[q] = m;
         float b;
         int st = 0;
-        if (total > a.cap || (a.status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }   // lost entries
+        if (lost || (a.status[q] & ST_OVERFLOW)) { b = INFINITY; st = ST_OVERFLOW; }   // lost entries
         else if (n > a.kprime) b = avs_key_score(key_kp);                 // rows outside the K' candidates <= K'-th key
         else if ((int64_t)n >= a.n_rows) b = -INFINITY;                   // every row is a candidate
         else b = a.tau[q] == 0ull ? -INFINITY : avs_key_score(a.tau[q]);  // rows outside < threshold
@@ -249,6 +250,57 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         }
         __syncthreads();                        // too many keys at the pivot (ties): full sort below
     }
+    // Dense buffer of the gemv path (up to 64 K keys, one CTA of 1024 threads per query) with a rank beyond the warp
+    // pivot path above: block pivot.  The rank-`want` value of the 1024 thread-local maxima is a lower bound of the
+    // rank-`want` key, so only the few keys above it (about `want` of them) are compacted into shared memory and
+    // sorted: two passes over the keys instead of the radix select's nine, which matters when a single query waits.
+    if (a.dense_src && blockDim.x == 1024 && n >= 4096 && (a.is_final ? a.kprime : a.j_rank) <= 512) {
+        __shared__ int s_bm, s_bnz;
+        const int nt = blockDim.x, tid = threadIdx.x;
+        const int want = a.is_final ? a.kprime : a.j_rank;
+        u64 lm = 0;
+        int nzc = 0;
+        for (int i = tid; i < n; i += nt) { const u64 key = cin[i]; lm = key > lm ? key : lm; nzc += key != 0ull; }
+        sm[tid] = lm;
+        if (tid == 0) { s_bm = 0; s_bnz = 0; }
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
+        if (lane == 0 && nzc) atomicAdd(&s_bnz, nzc);
+        bitonic_sort_desc(sm, 1024);                 // ends with a barrier: s_bnz is complete as well
+        const u64 Pv = sm[want - 1];
+        const int n_real = s_bnz;
+        __syncthreads();                             // everyone holds the pivot before the list overwrites sm
+        // final level: the wide-rescoring stage wants every real key in the candidate buffer when they fit -> radix path
+        const bool usable = Pv != 0ull && !(a.is_final && n_real <= a.cap);
+        if (usable) {
+            for (int i = tid; i < n; i += nt) {
+                const u64 key = cin[i];
+                if (key >= Pv) { const int pos = atomicAdd(&s_bm, 1); if (pos < a.cap) sm[pos] = key; }
+            }
+        }
+        __syncthreads();
+        const int m = s_bm;                          // >= want: the `want` largest local maxima are distinct keys
+        if (usable && m <= a.cap) {
+            int P2 = 32;
+            while (P2 < m) P2 <<= 1;
+            for (int i = m + tid; i < P2; i += nt) sm[i] = 0ull;
+            __syncthreads();
+            bitonic_sort_desc(sm, P2);
+            if (!a.is_final) {
+                for (int i = tid; i < want; i += nt) c[i] = sm[i];
+                if (tid == 0) { a.tau[qq] = sm[want - 1]; a.cnt[qq] = want; }
+            } else {
+                for (int i = tid; i < a.kprime; i += nt) a.topkeys[(size_t)qq * a.kprime + i] = sm[i];
+                if (tid == 0) {
+                    a.cnt[qq] = a.cap + 1;           // the collected set does not fit the candidate buffer: no wide stage
+                    select_emit_scalar(a, qq, n_real, n_real, sm[want - 1], sm[want - 1], false);
+                }
+            }
+            return;
+        }
+        __syncthreads();                             // few real keys (row filter) or too many above the pivot: radix select
+    }
     // Large collected sets (big K', many-row dense level): 8-pass byte-wise radix select of the rank-`want` key
     // straight from L2 (O(n) per pass, no 64-128 KB of shared memory) and an unordered compaction of the keys
     // above it.  Neither the next level nor the rescoring stage needs the survivors sorted.
@@ -272,8 +324,9 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
             total = n_real;
             __syncthreads();
         }
+        const bool lost = !a.dense_src && total > a.cap;   // the dense buffer holds every key of its level
         int jj = a.j_rank;
-        if (total > a.cap) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
+        if (lost) { jj = (int)(((long long)a.j_rank * a.cap) / total); if (jj < 1) jj = 1; }
         const int want = a.is_final ? (n_real < a.kprime ? n_real : a.kprime) : (n_real >= jj ? jj : n_real);
         u64 prefix = 0, maskb = 0;
         int rank = want - 1;
@@ -343,7 +396,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
         } else if (tid == 0) {
             a.cnt[qq] = a.dense_total > 0 ? n : total;   // dense level inside the buffer: slots (zero = empty), not keys
         }
-        if (tid == 0) select_emit_scalar(a, qq, total, n_real, Pk, Pk);
+        if (tid == 0) select_emit_scalar(a, qq, total, n_real, Pk, Pk, lost);
         return;
     }
     if (threadIdx.x == 0) s_nz = 0;
@@ -393,7 +446,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) c[i] = sm[i];   // sorted: the wide rescoring stage reads it
     if (threadIdx.x == 0) {
         a.cnt[qq] = total;
-        select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1]);
+        select_emit_scalar(a, qq, total, n, sm[jj - 1 < P ? jj - 1 : P - 1], sm[a.kprime - 1 < P ? a.kprime - 1 : P - 1], total > a.cap);
     }
 }
 
@@ -914,7 +967,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         double need = 0.0;
         for (int i = L - 2; i >= 0; --i) {
             const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
-            if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : s->opt_coarse_sigma) * sqrt((double)kprime * ratio);
+            if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : (use_gemm ? s->opt_coarse_sigma : 8)) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
             j_ranks[i] = (int)j;

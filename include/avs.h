@@ -119,7 +119,9 @@ int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out);
 int avs_p2p_connect(avs_store* s, const void* handles, int world);
 
 /* Options: "scan_path" 0=auto 1=gemv 2=gemm; "oversample" K' override (0=auto); "gemm_min_batch";
- * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant); "p2p_merge" 0|1; "force_repair" (testing: 1 = force the
+ * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant) and "cta_group_small" 1|2 (the variant for batches of at most
+ * 128 queries; default 1: M = 128 queries per CTA, half the padded MMA work); schedule knobs "fine_ratio",
+ * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "force_repair" (testing: 1 = force the
  * wide-rescoring stage, 2 = force the exact scan as well). */
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate

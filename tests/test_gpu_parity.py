@@ -65,6 +65,35 @@ def test_store_matches_oracle(pkg, metric, n, d, nq, k):
         st.close()
 
 
+@pytest.mark.parametrize("n,k", [(125_000, 10), (125_000, 100), (50_000, 10), (9_000, 50), (300_000, 50)])
+def test_small_batch_dense_level_is_not_an_overflow(pkg, n, k):
+    """gemv path (batch <= 2) with its 64 K-row threshold-free level held in the dense buffer.  Small stride ratios ask
+    for ranks beyond the warp pivot select (block pivot / radix select), and a store of at most 64 K rows is searched
+    in that single level.  Regression: the dense buffer's keys were measured against the candidate buffer's capacity,
+    which forced the exact repair scan on every query (1/8 C2 shard at batch 1: 0.74 ms instead of 0.1 ms)."""
+    d = 64
+    X, ids, Q = _data(n, d, 2, seed=n + k, scale=True)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        exp_ids, exp_d, exp_rows = fs.search_large(X, ids, Q, k, "COSINE")
+        for nq in (1, 2):
+            got_ids, got_d, got_rows = st.search(Q[:nq], k, return_rows=True)
+            assert st.stat("last_scan_path") == 1
+            _check(got_ids, got_d, exp_ids[:nq], exp_d[:nq])
+            assert np.array_equal(got_rows, exp_rows[:nq])
+        mask = np.zeros(n, dtype=bool)                      # row filter leaving fewer real keys than the rank asked for
+        mask[:: max(1, n // 300)] = True
+        st.set_filter(mask)
+        f_ids, f_d = st.search(Q[:1], k)
+        rows = np.nonzero(mask)[0]
+        ef_ids, ef_d, _ = fs.search(X[rows], ids[rows], Q[:1], k, "COSINE")
+        _check(f_ids, f_d, ef_ids, ef_d)
+        assert st.stat("uncertified_queries") == 0 and st.stat("repaired_queries") == 0
+    finally:
+        st.close()
+
+
 def test_multi_level_scan_and_device_tensor_api(pkg):
     """N large enough for three sampling levels; torch CUDA tensors in, device tensors out."""
     import torch
@@ -304,6 +333,7 @@ def test_tensor_core_scan_matches_oracle(pkg, cta_group, n, d, nq, k, metric):
         st.insert(X, ids)
         st.set_option("scan_path", 2)
         st.set_option("cta_group", cta_group)
+        st.set_option("cta_group_small", cta_group)            # batches <= 128 default to the single-CTA (M = 128) variant
         got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
         assert st.stat("last_scan_path") == 2
         exp_ids, exp_d, exp_rows = (fs.search_large if n > 20000 else fs.search)(X, ids, Q, k, metric)
@@ -327,8 +357,11 @@ def test_auto_path_switches_to_tensor_cores_and_agrees_with_gemv(pkg):
         assert st.stat("last_scan_path") == 1
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         st.set_option("scan_path", 0)
-        st.search(Q[:3], k)
-        assert st.stat("last_scan_path") == 1                  # 3 queries: HBM-bound warp-dot scan
+        st.search(Q[:2], k)
+        assert st.stat("last_scan_path") == 1                  # 2 queries: HBM-bound warp-dot scan
+        c3 = st.search(Q[:3], k)
+        assert st.stat("last_scan_path") == 2                  # measured crossover: the M=128 tensor-core scan wins from 3 queries on
+        assert np.array_equal(c3[0], a[0][:3]) and np.array_equal(c3[1], a[1][:3])
     finally:
         st.close()
 
