@@ -31,7 +31,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     for (n, d, nq, k, metric) in [(200_003, 256, 5, 10, "COSINE"), (150_000, 768, 96, 10, "COSINE"),
-                                  (64_000, 128, 300, 100, "IP"), (1000, 64, 3, 50, "COSINE")]:
+                                  (64_000, 128, 300, 100, "IP"), (1000, 64, 3, 50, "COSINE"),
+                                  (250_000, 128, 1, 10, "COSINE"), (250_000, 128, 2, 100, "COSINE")]:   # gemv, dense 64 K-row level
         ss = sharded.ShardedStore(d, metric, n, rank, world, device=local)
         ss.fill_synthetic(42)
         Q = synth.planted_queries(43, 42, n, nq, d)
