@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
         const double acc_v = (((double)dpad / 32.0 + 8.0) * 1.2e-7 + 1e-6) * n_f * xmax;
         const double acc_m = ((double)dpad * 1.2e-7 + 1e-6) * n_b * xmax;
         qnorm[qi] = qn;
-        eps_gemv[qi] = (float)(n_f * r_max + acc_v);
-        eps_gemm[qi] = (float)(n_b * r_max + e_q * xmax + acc_m);
+        const float e_v = (float)(n_f * r_max + acc_v), e_m = (float)(n_b * r_max + e_q * xmax + acc_m);
+        eps_gemv[qi] = e_v;
+        eps_gemm[qi] = fmaxf(e_m, e_v);   // the hybrid small-batch pipeline mixes both scans under this one slack
         tau[qi] = 0ull;
         cnt[qi] = 0;
         status[qi] = 0;
@@ -917,7 +918,12 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         return AVS_OK;
     }
 
-    const bool use_gemm = (s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch);
+    // Small batches in auto mode (at most 8 queries = one gemv pass): hybrid pipeline.  The threshold-free level is the
+    // gemv path's (up to 64 K rows stored densely in its own buffer: one level fewer than the tensor-core schedule),
+    // every later level streams through the single-CTA tensor-core scan, whose TMA bulk loads sustain more of the HBM
+    // bandwidth than the warp-dot kernel does.  Schedule and level-0 kernel are the gemv path's (use_gemm = false).
+    const bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 && nq <= 8;
+    const bool use_gemm = !hybrid && ((s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch));
     // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
     // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
@@ -967,7 +973,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         double need = 0.0;
         for (int i = L - 2; i >= 0; --i) {
             const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
-            if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : (use_gemm ? s->opt_coarse_sigma : 8)) * sqrt((double)kprime * ratio);
+            if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : ((use_gemm || hybrid) ? s->opt_coarse_sigma : 8)) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
             j_ranks[i] = (int)j;
@@ -978,13 +984,16 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;
     s->st_last_kprime = kprime;
     s->st_last_levels = L;
-    s->st_last_path = use_gemm ? 2 : 1;
+    const bool hybrid_on = hybrid && L > 1 && lv[0].dense;   // single-level searches stay on the gemv kernels
+    const bool any_gemm = use_gemm || hybrid_on;
+    const float* eps_used = any_gemm ? c.eps_gemm : c.eps_gemv;   // prep makes eps_gemm >= eps_gemv
+    s->st_last_path = any_gemm ? 2 : 1;
 
     // Adaptive policy, no host synchronisation: the counters of earlier searches arrive in pinned memory whenever
     // their copy executes.  Once a query needed the exact repair scan (large dims: eps is big against the score
     // spacing), the last threshold is kept 2.5 eps under the k-th score so that wide rescoring suffices.
     if (s->h_stats && s->h_stats[0] > s->seen_repaired) { s->seen_repaired = s->h_stats[0]; s->eps_rule = true; }
-    const int n_slots = use_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
+    const int n_slots = any_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
     prep_queries_kernel<<<n_slots, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
                                                 c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status, c.flagged, c.flagged2);
     s->st_launches++;
@@ -1004,7 +1013,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         const bool final_level = (l == L - 1);
         size_t slot = 0;
         const bool timed = final_level && timing_begin(s, st, &slot);
-        if (use_gemm) {
+        if (use_gemm || (hybrid_on && l > 0)) {
             AVS_CHECK(avs_launch_scan_gemm(s, nq, lv[l], cap, st));
         } else {
             for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
@@ -1013,19 +1022,19 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, n_eff, c.topkeys, c.topn,
                          bound, c.status, lv[l].dense ? (int)(lv[l].n_visit * AVS_GROUP_ROWS) : 0, nq,
                          (lv[l].dense && !use_gemm) ? c.dense_buf : nullptr, AVS_DENSE_CAP,
-                         use_gemm ? c.eps_gemm : c.eps_gemv, (l == L - 2 && fine_levels && s->eps_rule) ? k : 0};
+                         eps_used, (l == L - 2 && fine_levels && s->eps_rule) ? k : 0};
         select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
     }
 
-    finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, use_gemm ? c.eps_gemm : c.eps_gemv, kprime, k,
+    finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
                                         n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
                                         c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
     wide_rescore_kernel<<<nq, 1024, AVS_WIDE_MAX * sizeof(Hit), st>>>(
-        s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, use_gemm ? c.eps_gemm : c.eps_gemv, k,
+        s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, eps_used, k,
         n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
         c.rep_cnt, s->dstat);
     s->st_launches++;
@@ -1109,6 +1118,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "p2p_merge") s->opt_p2p = value != 0;
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
+    else if (k == "hybrid") s->opt_hybrid = value != 0;
     else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;
     else if (k == "coarse_sigma") s->opt_coarse_sigma = value < 1 ? 1 : (int)value;
     else if (k == "cta_group_small") s->opt_cta_group_small = value == 1 ? 1 : 2;

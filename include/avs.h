@@ -118,7 +118,8 @@ int avs_search_sharded(avs_store* s, const float* q, int nq, int k,
 int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out);
 int avs_p2p_connect(avs_store* s, const void* handles, int world);
 
-/* Options: "scan_path" 0=auto 1=gemv 2=gemm; "oversample" K' override (0=auto); "gemm_min_batch";
+/* Options: "scan_path" 0=auto 1=gemv 2=gemm; "hybrid" 0|1 (auto mode, <= 8 queries: dense warp-dot level, tensor-core
+ * scan for the later levels; default 1); "oversample" K' override (0=auto); "gemm_min_batch";
  * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant) and "cta_group_small" 1|2 (the variant for batches of at most
  * 128 queries; default 1: M = 128 queries per CTA, half the padded MMA work); schedule knobs "fine_ratio",
  * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "force_repair" (testing: 1 = force the

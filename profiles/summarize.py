@@ -1,6 +1,6 @@
 """Turns the .ncu-rep captures brought back in gpurun_out/ into the committed summaries under profiles/.
 
-    python profiles/summarize.py r01
+    python profiles/summarize.py r01 [subdirectory of gpurun_out/]
 
 Writes, per capture, the metrics the roofline claims rest on (duration, DRAM bytes, tensor-pipe activity,
 registers, clocks) as `profiles/<round>/<name>.metrics.txt`, the per-launch list of one default bench.py run as
@@ -31,10 +31,13 @@ def raw_metrics(rep):
     return {h: (v, u) for h, v, u in zip(hdr, vals, units)}
 
 
-def main(rnd):
-    src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles", rnd)
+def main(rnd, sub=""):
+    src, dst = os.path.join(ROOT, "gpurun_out", sub), os.path.join(ROOT, "profiles", rnd)
     os.makedirs(dst, exist_ok=True)
-    traffic = {}
+    try:                                   # captures are not repeated every run: keep the entries already committed
+        traffic = json.load(open(os.path.join(dst, "traffic.json")))
+    except Exception:
+        traffic = {}
     for name, key in (("prof_k3_final", "scan_gemm"), ("prof_k2_final", "scan_gemv"), ("prof_k1", "normalize_rows")):
         rep = os.path.join(src, name + ".ncu-rep")
         if not os.path.exists(rep):
@@ -74,4 +77,4 @@ def main(rnd):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "r01")
+    main(sys.argv[1] if len(sys.argv) > 1 else "r01", sys.argv[2] if len(sys.argv) > 2 else "")

@@ -3,7 +3,7 @@
     compute-sanitizer --tool memcheck python tests/sanitizer_check.py
 
 Exercises every kernel once on small shapes: insert (both normalise kernels), gemv and tensor-core scans with
-several levels, dense level, pivot / bitonic / radix selects, finalize, wide rescoring, exact repair, row filter.
+several levels, dense level, warp-pivot / block-pivot / bitonic / radix selects, single-CTA and CTA-pair tensor-core scans, finalize, wide rescoring, exact repair, row filter.
 """
 import importlib
 import os
@@ -22,7 +22,8 @@ def main():
     rng = np.random.default_rng(0)
     ok = True
     for (n, d, nq, k, metric, force) in [(6000, 64, 2, 10, "COSINE", 0), (6000, 64, 40, 10, "COSINE", 0), (5000, 100, 20, 100, "IP", 0),
-                                         (3000, 6148, 3, 5, "COSINE", 0), (4000, 64, 5, 10, "COSINE", 2), (40000, 32, 260, 10, "COSINE", 1)]:
+                                         (3000, 6148, 3, 5, "COSINE", 0), (4000, 64, 5, 10, "COSINE", 2), (40000, 32, 260, 10, "COSINE", 1),
+                                         (130000, 32, 1, 100, "COSINE", 0), (9000, 32, 2, 50, "IP", 0), (70000, 64, 100, 10, "COSINE", 0)]:
         X = rng.standard_normal((n, d)).astype(np.float32)
         Q = rng.standard_normal((nq, d)).astype(np.float32)
         ids = np.arange(n, dtype=np.int64)

@@ -65,8 +65,9 @@ def test_store_matches_oracle(pkg, metric, n, d, nq, k):
         st.close()
 
 
+@pytest.mark.parametrize("scan_path", [0, 1])
 @pytest.mark.parametrize("n,k", [(125_000, 10), (125_000, 100), (50_000, 10), (9_000, 50), (300_000, 50)])
-def test_small_batch_dense_level_is_not_an_overflow(pkg, n, k):
+def test_small_batch_dense_level_is_not_an_overflow(pkg, n, k, scan_path):
     """gemv path (batch <= 2) with its 64 K-row threshold-free level held in the dense buffer.  Small stride ratios ask
     for ranks beyond the warp pivot select (block pivot / radix select), and a store of at most 64 K rows is searched
     in that single level.  Regression: the dense buffer's keys were measured against the candidate buffer's capacity,
@@ -76,10 +77,11 @@ def test_small_batch_dense_level_is_not_an_overflow(pkg, n, k):
     st = pkg.Store(d, "COSINE", capacity=n)
     try:
         st.insert(X, ids)
+        st.set_option("scan_path", scan_path)               # 0: hybrid (dense warp-dot level, tensor-core final level); 1: warp-dot only
         exp_ids, exp_d, exp_rows = fs.search_large(X, ids, Q, k, "COSINE")
         for nq in (1, 2):
             got_ids, got_d, got_rows = st.search(Q[:nq], k, return_rows=True)
-            assert st.stat("last_scan_path") == 1
+            assert st.stat("last_scan_path") == (2 if scan_path == 0 and n > 65536 else 1)
             _check(got_ids, got_d, exp_ids[:nq], exp_d[:nq])
             assert np.array_equal(got_rows, exp_rows[:nq])
         mask = np.zeros(n, dtype=bool)                      # row filter leaving fewer real keys than the rank asked for
@@ -357,11 +359,13 @@ def test_auto_path_switches_to_tensor_cores_and_agrees_with_gemv(pkg):
         assert st.stat("last_scan_path") == 1
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         st.set_option("scan_path", 0)
-        st.search(Q[:2], k)
-        assert st.stat("last_scan_path") == 1                  # 2 queries: HBM-bound warp-dot scan
         c3 = st.search(Q[:3], k)
-        assert st.stat("last_scan_path") == 2                  # measured crossover: the M=128 tensor-core scan wins from 3 queries on
+        assert st.stat("last_scan_path") == 1                  # <= 8 queries, <= 64 K rows: one dense warp-dot level
         assert np.array_equal(c3[0], a[0][:3]) and np.array_equal(c3[1], a[1][:3])
+        st.set_option("hybrid", 0)
+        c9 = st.search(Q[:3], k)
+        assert st.stat("last_scan_path") == 2                  # without the hybrid pipeline: tensor-core scan from 3 queries on
+        assert np.array_equal(c9[0], a[0][:3]) and np.array_equal(c9[1], a[1][:3])
     finally:
         st.close()
 
