@@ -922,7 +922,12 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // gemv path's (up to 64 K rows stored densely in its own buffer: one level fewer than the tensor-core schedule),
     // every later level streams through the single-CTA tensor-core scan, whose TMA bulk loads sustain more of the HBM
     // bandwidth than the warp-dot kernel does.  Schedule and level-0 kernel are the gemv path's (use_gemm = false).
-    const bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 && nq <= 8;
+    // Measured (profiles/r01/hybrid_*.json): for 1-2 queries the tensor-core scan streams D <= 1024 rows 3-14 % faster than
+    // the warp-dot kernel and loses 5 % at D = 3072; for 3-8 queries the level saved (~35 us) pays off while the final
+    // scan is short (C2: +10 %, 125 K-row shard: +37 %) but not on 20 GB shards, where the plain tensor-core schedule stays.
+    const size_t scan_bytes = (size_t)s->count * s->dpad * 2;
+    const bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 &&
+                        ((nq <= 2 && s->dpad <= 1024) || (nq >= 3 && nq <= 8 && scan_bytes <= ((size_t)8 << 30)));
     const bool use_gemm = !hybrid && ((s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch));
     // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with

@@ -227,7 +227,8 @@ def ncu_traffic(a, batch, path):
     import glob
     if (a.rows, a.dim, a.k) != (1_000_000, 768, 10):
         return None
-    key = "scan_gemm" if (path == 2 and batch == 1024) else "scan_gemv" if (path == 1 and batch == 1) else None
+    key = ("scan_gemm" if (path == 2 and batch == 1024) else "scan_gemm_m128_b1" if (path == 2 and batch == 1)
+           else "scan_gemm_m128" if (path == 2 and batch == 64) else "scan_gemv" if (path == 1 and batch == 1) else None)
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")))
     if not key or not files:
         return None

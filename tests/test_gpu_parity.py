@@ -163,6 +163,8 @@ def test_repair_path_is_exact(pkg):
     st = pkg.Store(d, "COSINE", capacity=n)
     try:
         st.insert(X, ids)
+        st.set_option("hybrid", 0)                             # 5 queries on the tensor-core schedule (the hybrid small-batch
+        #                                                        pipeline would search 9000 rows in one dense warp-dot level)
         st.set_option("force_repair", 1)                       # stage 1: wide rescoring of the collected set
         got_ids, got_d = st.search(Q, k)
         _check(got_ids, got_d, exp_ids, exp_d)
