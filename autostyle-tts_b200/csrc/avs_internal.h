@@ -163,6 +163,7 @@ struct avs_store {
     int opt_fine_min_batch = 129;    // tensor-core path: batches from here on use the fine (x4) dense-end schedule
     int opt_coarse_sigma = 3;        // same margin for the coarse (x32) schedule of the tensor-core path (gemv: 8)
     int opt_cta_group_small = 1;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
+    int opt_dense_rows = AVS_DENSE_CAP;   // rows of the gemv path's threshold-free level (<= AVS_DENSE_CAP)
     int opt_hybrid = 1;              // auto mode, <= 8 queries: gemv dense level, tensor-core scan for the later levels
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;

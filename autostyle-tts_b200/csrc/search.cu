@@ -942,7 +942,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // the threshold-free level: <= 2048 rows inside the candidate buffer on the tensor-core path; the gemv path (few
     // queries) stores up to 64 K rows densely in its own buffer, which saves it a whole intermediate level
     const bool dense_gemv = !use_gemm && nq <= AVS_DENSE_MAX_NQ;
-    const int64_t level0_rows = dense_gemv ? AVS_DENSE_CAP : (cap < 2048 ? cap : 2048);
+    const int64_t level0_rows = dense_gemv ? s->opt_dense_rows : (cap < 2048 ? cap : 2048);
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
@@ -1124,6 +1124,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
+    else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);
     else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;
     else if (k == "coarse_sigma") s->opt_coarse_sigma = value < 1 ? 1 : (int)value;
     else if (k == "cta_group_small") s->opt_cta_group_small = value == 1 ? 1 : 2;

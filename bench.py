@@ -308,6 +308,19 @@ def run_ours(a):
             ms = float(t.item())
         return ms / steps, (t_lo, t_hi)
 
+    def per_step_latency(fn, n):
+        """p10 / median / p90 of single search calls, each bracketed by its own CUDA events."""
+        out = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        p10, p50, p90 = (float(x) for x in np.percentile(out, [10, 50, 90]))
+        return {"p10": p10, "p50": p50, "p90": p90, "calls": n}
+
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
@@ -323,6 +336,7 @@ def run_ours(a):
         ms, win = timed(fn_dev, a.steps, a.warmup)
         launches = (st.stat("kernel_launches") - l0) // (a.steps + a.warmup) * a.steps
         scan_ms, scan_n = st.scan_timing(0)
+        lat = per_step_latency(fn_dev, max(5, min(a.steps, 30)))
         windows.append(win)
         dev_window = len(windows) - 1
         path, levels = st.stat("last_scan_path"), st.stat("last_levels")
@@ -368,7 +382,7 @@ def run_ours(a):
             e2e = {"value": batch / (ms_e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e,
                    "h2d_bytes_per_step": int(batch * a.dim * 4), "d2h_bytes_per_step": int(batch * a.k * 12),
                    "api": "avs_search_sharded (pinned H2D, D2H of ids+scores)"}
-        results[batch] = {"dev_window": dev_window, "qps": batch / (ms * 1e-3), "ms": ms, "launches": int(launches), "roofline": roof, "e2e": e2e,
+        results[batch] = {"dev_window": dev_window, "latency_ms": lat, "qps": batch / (ms * 1e-3), "ms": ms, "launches": int(launches), "roofline": roof, "e2e": e2e,
                           "scan_path": path, "levels": levels, "kprime": st.stat("last_kprime")}
     # size-independent parity property at any scale: a query planted next to database row j must retrieve id j first
     planted_ok = None
@@ -389,6 +403,13 @@ def run_ours(a):
                "sample": f"{nq_cpu} of {a.batch} queries x all {rows_local} rows, mean of 8 passes ({dt:.2f} s each), numpy fp32 sgemm + argpartition"}
         dt1 = cpu_flat_time(X, Qh[:1], a.k, reps=20)
         cpu["batch1_value"] = 1.0 / dt1
+        cpu["host_cpu_count"] = os.cpu_count()
+        try:                                   # the 1-core figure next to the all-cores one
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                cpu["value_1core"] = 16 / cpu_flat_time(X, Qh[:16], a.k)
+        except Exception:
+            cpu["value_1core"] = None
         # parity spot-check of the bench workload itself against the float64 oracle
         from oracle import flat_search as fs
         exp_ids, _, _ = fs.search_large(X, np.arange(rows_local), Qh[:8], a.k, a.metric)
@@ -418,12 +439,12 @@ def run_ours(a):
                            "arith": "bf16 operands, fp32 accumulate scan; float64 rescoring of the candidates",
                            "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],
                            "oversample_kprime": main["kprime"]},
-                "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
+                "latency_ms": main["latency_ms"], "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
                 "cpu_baseline": cpu, "planted_top1_match": planted_ok, "uncertified_queries": unc, "repaired_queries": rep,
                 "wide_rescored_queries": wide}
         if 1 in results and a.batch != 1:
             b1 = results[1]
-            line["batch1"] = {"value": b1["qps"], "unit": "queries/s", "ms_per_step": b1["ms"], "e2e": b1["e2e"],
+            line["batch1"] = {"value": b1["qps"], "unit": "queries/s", "ms_per_step": b1["ms"], "latency_ms": b1["latency_ms"], "e2e": b1["e2e"],
                               "gpu_launches": b1["launches"], "roofline": b1["roofline"]}
         if sweep:
             line["sweep"] = [{"batch": b, "value": results[b]["qps"], "ms_per_step": results[b]["ms"],
