@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WANT = ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active_realtime",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg", "sm__pipe_tensor_cycles_active_realtime", "dram__cycles_active.avg",
         "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max.per_second",
         "derived__lts__lts2xbar_bytes.sum.per_second", "sm__warps_active.avg.pct_of_peak_sustained_active",
