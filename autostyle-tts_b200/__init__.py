@@ -5,8 +5,8 @@ The directory name carries a hyphen, so import it through the `autostyle_tts_b20
 the repository root (or `importlib.import_module("autostyle-tts_b200")`).
 """
 from .client import MAX_LIMIT, MilvusClient
-from .engine import ABI_SYMBOLS, LIB_PATH, AvsError, Store, load_library
+from .engine import ABI_SYMBOLS, LIB_PATH, AvsError, ExactnessWarning, Store, load_library
 from .schema import CollectionSchema, DataType, FieldSchema, IndexParams, MilvusException
 
 __all__ = ["MilvusClient", "FieldSchema", "CollectionSchema", "DataType", "IndexParams", "MilvusException",
-           "Store", "AvsError", "load_library", "ABI_SYMBOLS", "LIB_PATH", "MAX_LIMIT"]
+           "Store", "AvsError", "ExactnessWarning", "load_library", "ABI_SYMBOLS", "LIB_PATH", "MAX_LIMIT"]

@@ -138,6 +138,8 @@ struct avs_store {
     size_t filter_words = 0;          // allocated words
     float* gstat = nullptr;           // [4] device scalars: r_max, xnorm_max (non-negative, atomicMax on bits)
     unsigned long long* dstat = nullptr;  // [8] device counters: repaired, uncertified, wide-rescored
+    unsigned long long seen_uncertified = 0;   // h_stats[1] at the end of the previous avs_search_host call
+    int64_t st_last_uncertified = 0;           // queries of the last avs_search_host call whose top-k could not be proven
     unsigned long long* h_stats = nullptr;  // pinned host mirror of dstat, refreshed asynchronously after every search
     unsigned long long seen_repaired = 0;
     bool eps_rule = false;            // set once an exact repair was needed: the last threshold then honours eps

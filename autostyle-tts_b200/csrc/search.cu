@@ -1105,6 +1105,10 @@ extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k,
     const size_t out_bytes = items * (2 * sizeof(int64_t) + sizeof(float));
     AVS_CUDA(cudaMemcpyAsync(c.h_out, c.d_ids, out_bytes, cudaMemcpyDeviceToHost, st));
     AVS_CUDA(cudaStreamSynchronize(st));
+    if (s->h_stats) {   // the mirror copy of the counters was enqueued before the result copy: current after the sync
+        s->st_last_uncertified = (int64_t)(s->h_stats[1] - s->seen_uncertified);
+        s->seen_uncertified = s->h_stats[1];
+    }
     memcpy(out_ids_host, c.h_out, items * sizeof(int64_t));
     if (out_rows_host) memcpy(out_rows_host, c.h_out + items, items * sizeof(int64_t));
     memcpy(out_scores_host, c.h_out + 2 * items, items * sizeof(float));
@@ -1143,6 +1147,7 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "last_final_rows") *out = s->st_last_final_rows;
     else if (k == "p2p_timeouts") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_timeouts(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
+    else if (k == "last_uncertified") *out = s->st_last_uncertified;   // of the last avs_search_host call; no device sync
     else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries") {
         AVS_CUDA(cudaSetDevice(s->device));
         u64 h[3];

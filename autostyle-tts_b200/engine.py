@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import warnings
 from typing import Optional
 
 import numpy as np
@@ -37,6 +38,10 @@ class AvsError(RuntimeError):
         super().__init__(f"[avs {code}] {message}")
         self.code = code
         self.message = message
+
+
+class ExactnessWarning(UserWarning):
+    """A search returned hits whose exactness certificate could not be established (see avs_get_stat)."""
 
 
 _lib = None
@@ -205,6 +210,10 @@ class Store:
         rows = np.empty((nq, k), dtype=np.int64)
         _check(self._lib, self._lib.avs_search_host(self._h, q.ctypes.data, nq, int(k), ids.ctypes.data, sc.ctypes.data,
                                                     rows.ctypes.data))
+        unproven = self.stat("last_uncertified")
+        if unproven:
+            warnings.warn(f"{unproven} of {nq} queries have more than 4096 rows tied with their k-th score: the hits returned "
+                          "for them are best matches, but the tie order by primary key is not proven", ExactnessWarning)
         return (ids, sc, rows) if return_rows else (ids, sc)
 
     def set_filter(self, mask):

@@ -127,7 +127,9 @@ int avs_p2p_connect(avs_store* s, const void* handles, int world);
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
- * "uncertified_queries", "p2p_timeouts", "last_kprime", "last_levels", "last_scan_path", "last_final_rows". */
+ * "uncertified_queries", "p2p_timeouts", "last_kprime", "last_levels", "last_scan_path", "last_final_rows";
+ * "last_uncertified": queries of the last avs_search_host call whose top-k could not be proven exact (more than 4096
+ * rows tied with the k-th score) - read without a device synchronisation. */
 int avs_get_stat(avs_store* s, const char* key, int64_t* out);
 
 /* Timing hook for bench.py: when enabled, CUDA events bracket the dominant scan
