@@ -21,9 +21,12 @@ pkg = importlib.import_module("autostyle-tts_b200")
 def main():
     rng = np.random.default_rng(0)
     ok = True
-    for (n, d, nq, k, metric, force) in [(6000, 64, 2, 10, "COSINE", 0), (6000, 64, 40, 10, "COSINE", 0), (5000, 100, 20, 100, "IP", 0),
+    only = [int(x) for x in os.environ.get("SAN_CASES", "").split(",") if x.strip()]   # e.g. SAN_CASES=6,7 for racecheck
+    for case, (n, d, nq, k, metric, force) in enumerate([(6000, 64, 2, 10, "COSINE", 0), (6000, 64, 40, 10, "COSINE", 0), (5000, 100, 20, 100, "IP", 0),
                                          (3000, 6148, 3, 5, "COSINE", 0), (4000, 64, 5, 10, "COSINE", 2), (40000, 32, 260, 10, "COSINE", 1),
-                                         (130000, 32, 1, 100, "COSINE", 0), (9000, 32, 2, 50, "IP", 0), (70000, 64, 100, 10, "COSINE", 0)]:
+                                         (130000, 32, 1, 100, "COSINE", 0), (9000, 32, 2, 50, "IP", 0), (70000, 64, 100, 10, "COSINE", 0)]):
+        if only and case not in only:
+            continue
         X = rng.standard_normal((n, d)).astype(np.float32)
         Q = rng.standard_normal((nq, d)).astype(np.float32)
         ids = np.arange(n, dtype=np.int64)
