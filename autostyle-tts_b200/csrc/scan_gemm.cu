@@ -30,6 +30,7 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr int TAU_CACHE = 2048;         // thresholds of every query the CTA sweeps, cached in smem
 constexpr int STASH = 8;                // per-thread survivor stash (keys) between slot reservations
+static_assert(STASH == 8, "the dense level's transpose stages 32 queries x 8 keys in a warp's share of the stash");
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -291,12 +292,32 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // compare against the threshold; only a qualifying chunk builds the bit mask of its survivors.
             auto process = [&](const uint32_t (&v)[32], int col0) {
                 if (lv.dense) {
+                    // A lane owns one query's 32 scores, and the query's keys are contiguous in memory: stored lane by
+                    // lane, every store instruction would touch 32 sectors for 8 bytes each (1 K LSU transactions per
+                    // warp and chunk; the 2 048-row level cost 36 us that way).  So the warp transposes 32 queries x 8
+                    // keys at a time through its 2 KB of the (idle) survivor stash, XOR-swizzled so that neither side
+                    // has bank conflicts, and stores 4 queries x 64 contiguous bytes per instruction.
                     const uint32_t allow = filt ? filt[(row0 + col0) >> 5] : ~0u;   // the chunk's 32 rows = one bitmap word
-                    u64* dst = my_cand + (size_t)m * BLOCK_N + half * 128 + col0;
+                    u64* const stage = stash_smem + (size_t)(warp - 4) * 32 * STASH;
+                    const int rq = lane >> 3, rc = lane & 7;                       // reader role: query 4j + rq, key rc of the slice
+                    u64* const gbase = cand + (size_t)(q - lane) * cap + (size_t)m * BLOCK_N + half * 128 + col0;
+                    const bool live = tau_k != ~0ull;                              // padding query slots keep empty keys
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        dst[i] = (col0 + i < valid_cols && tau_k != ~0ull && ((allow >> i) & 1u))
-                                     ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
+                    for (int sl = 0; sl < 4; ++sl) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int i = 8 * sl + c;
+                            const u64 key = (col0 + i < valid_cols && live && ((allow >> i) & 1u))
+                                                ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
+                            stage[lane * STASH + (c ^ ((lane >> 1) & 7))] = key;
+                        }
+                        __syncwarp();
+                        u64* gp = gbase + (size_t)rq * cap + 8 * sl + rc;
+#pragma unroll 1
+                        for (int r = rq; r < 32; r += 4, gp += (size_t)4 * cap)   // kept rolled: the kernel sits at its register limit
+                            *gp = stage[r * STASH + (rc ^ ((r >> 1) & 7))];
+                        __syncwarp();
+                    }
                     return;
                 }
                 float gm[4];
