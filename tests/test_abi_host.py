@@ -227,6 +227,7 @@ def test_bench_reference_arm_runs_offline():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "3000", "--dim", "64",
                           "--steps", "1", "--warmup", "1", "--batch", "16"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert len(out.stdout.strip().splitlines()) == 1, "the contract is ONE JSON line on stdout"
+    line = json.loads(out.stdout.strip())
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "queries/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
