@@ -1,6 +1,9 @@
 // Search pipeline around the scan kernels:
 //   prep_queries -> [scan level l -> select level l]* -> finalize (float64 rescoring of K' + certificate)
 //   -> wide_rescore -> repair_scan / repair_finalize (device-gated: exit at once unless a query was flagged)
+// Which kernel scans a level (avs_search_local): the tensor-core scan (K3) for every level of a batch of 9+ queries;
+// for <= 8 queries the hybrid pipeline - threshold-free level on the warp-dot kernel (K2, up to 64 K rows kept densely),
+// later levels on K3's single-CTA variant; K2 alone for 1-2 queries of D > 1024 and for stores of <= 64 K rows.
 // Replaces the arithmetic behind `MilvusClient.search`
 // (/root/reference/milvus/search_embeddings.py:15-22, /root/reference/milvus/RAG.py:383-390).
 #include <math.h>
