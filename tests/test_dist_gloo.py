@@ -59,3 +59,23 @@ def test_sharded_merge_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches the reference arm like ours (torchrun, N ranks): rank 0 alone works and prints the
+    ONE JSON line, the other ranks exit 0 without output."""
+    import json
+    import subprocess
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--rows", "3000",
+           "--dim", "64", "--batch", "16", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
