@@ -406,11 +406,7 @@ class MilvusClient:
         if cached is not None and cached.shape[0] == len(coll.pks):
             return cached
         pred = compile_filter(expr)
-        mask = np.zeros(len(coll.pks), dtype=bool)
-        for r, pk in enumerate(coll.pks):
-            fields = dict(coll.meta[r])
-            fields[coll.pk_name] = pk
-            mask[r] = pred(fields)
+        mask = np.asarray(pred.rows(coll.meta, coll.pk_name, coll.pks), dtype=bool)
         if len(coll.filter_cache) >= 16:
             coll.filter_cache.pop(next(iter(coll.filter_cache)))
         coll.filter_cache[expr] = mask

@@ -181,3 +181,6 @@ int avs_scratch_reserve(avs_store* s, int nq, int kprime, int cap, int k);
 void avs_scratch_free(avs_store* s);
 void avs_comm_free(avs_store* s);
 int avs_p2p_timeouts(avs_store* s, int64_t* out);
+int avs_p2p_exchange_us(avs_store* s, int64_t* out);
+void avs_p2p_timing_reset(avs_store* s);
+int avs_host_staging_reserve(avs_store* s, int nq, int k);

@@ -105,23 +105,31 @@ __global__ void __launch_bounds__(256) shard_merge_kernel(const GatherItem* __re
 
 // ---------------------------------------------------------------------------------------------
 // Fused exchange + merge over NVLink peer memory (replaces pack -> ncclAllGather -> merge when connected).
-// Every rank exposes one exchange region through CUDA IPC.  One kernel per search, one CTA per query:
-//   1. store this rank's k (score, id) items of the query straight into slot [rank] of EVERY peer's region
-//      (remote stores over NVLink) and of its own,
-//   2. __threadfence_system, then publish flag[rank][q] = seq in every region,
-//   3. spin until the local region shows seq for the query from every rank,
-//   4. merge world*k items by (score desc, id asc) and write the global top-k.
-// A CTA pushes before it waits and never depends on another local CTA, so any scheduling order completes.
-// Two parities alternate between searches: a rank can only be one search ahead of its slowest peer (it needs
-// that peer's push to finish its own merge), so a region is never overwritten while it is still being read.
+// Every rank exposes one exchange region through CUDA IPC.  One kernel per search; its grid is never larger than
+// what the device keeps resident at once, so no CTA ever waits for a CTA that has not been scheduled:
+//   phase 1 (all of this CTA's queries, grid-stride): store this rank's k (score, id) items of the query straight
+//            into slot [rank] of EVERY peer's region (remote stores over NVLink) and of its own,
+//            __threadfence_system, publish flag[rank][q] = seq in every region;
+//   phase 2 (same queries): spin until the local region shows seq for the query from every rank, merge world*k
+//            items by (score desc, id asc), write the global top-k.
+// Every CTA of every rank finishes phase 1 without waiting for anybody, hence every wait of phase 2 completes
+// whatever the dispatch order.  Two parities alternate between searches: a rank can only be one search ahead of
+// its slowest peer (it needs that peer's push to finish its own merge), so a region is never overwritten while it
+// is still being read.  A spin that gives up (a peer died) poisons the query's output (id -1, score -inf) and
+// bumps `timeouts`, which the host mirrors into pinned memory: the next call fails with AVS_E_NCCL.
 // ---------------------------------------------------------------------------------------------
 #define P2P_MAX_WORLD 8
 #define P2P_ITEMS_PER_SRC (1 << 18)          // (score, id) items per source rank per parity (4 MiB)
 #define P2P_MAX_NQ (1 << 14)
+#define P2P_Q_FLOATS (1 << 23)               // query all-gather buffer per parity (32 MiB of fp32)
+#define P2P_Q_CTAS 128                       // CTAs of the query all-gather kernel (one completion flag each)
+#define P2P_SPIN_LIMIT (1ll << 27)
 
 struct P2PRegion {                            // layout of one rank's exchange region
     GatherItem items[2][P2P_MAX_WORLD][P2P_ITEMS_PER_SRC];
     unsigned int flags[2][P2P_MAX_WORLD][P2P_MAX_NQ];
+    float qbuf[2][P2P_Q_FLOATS];              // the query batch, every rank's slice pushed by its owner
+    unsigned int qflags[2][P2P_MAX_WORLD][P2P_Q_CTAS];
     unsigned int timeouts;
 };
 struct P2PPeers { P2PRegion* r[P2P_MAX_WORLD]; };
@@ -130,7 +138,12 @@ struct P2PState {
     P2PRegion* local = nullptr;
     P2PPeers peers{};
     bool connected = false;
-    unsigned int seq = 0;
+    unsigned int seq = 0, qseq = 0;
+    unsigned int* h_timeouts = nullptr;       // pinned mirror of local->timeouts, refreshed after every exchange
+    unsigned int seen_timeouts = 0;
+    int max_ctas = 0;                         // co-resident CTAs of the exchange kernel on this device
+    std::vector<cudaEvent_t> tev;             // event pairs around the exchange kernel (timing hook)
+    size_t tev_used = 0;
 };
 
 __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers, int rank, int world, unsigned int seq,
@@ -138,69 +151,112 @@ __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers,
                                                                  int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     extern __shared__ unsigned char raw[];
     GatherItem* sm = reinterpret_cast<GatherItem*>(raw);
-    const int q = blockIdx.x, par = seq & 1;
-    const size_t slot = (size_t)q * k;
-    // 1. push my items for this query into every region (mine included)
-    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
-        const int r = i / k, t = i - r * k;
-        GatherItem it;
-        it.s = s64[slot + t];
-        it.id = out_ids[slot + t];
-        peers.r[r]->items[par][rank][slot + t] = it;
+    __shared__ int s_dead;
+    const int par = seq & 1;
+    // phase 1: push my items of every query this CTA owns into every region (mine included), then publish
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        const size_t slot = (size_t)q * k;
+        for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+            const int r = i / k, t = i - r * k;
+            GatherItem it;
+            it.s = s64[slot + t];
+            it.id = out_ids[slot + t];
+            peers.r[r]->items[par][rank][slot + t] = it;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world) {
+            volatile unsigned int* f = &peers.r[threadIdx.x]->flags[par][rank][q];
+            *f = seq;
+        }
+    }
+    // phase 2: wait for every rank's items of my queries in MY region (bounded spin: a missing peer must not hang the GPU)
+    P2PRegion* mine = peers.r[rank];
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        const size_t slot = (size_t)q * k;
+        if (threadIdx.x == 0) s_dead = 0;
+        __syncthreads();
+        if (threadIdx.x < world) {
+            volatile unsigned int* f = &mine->flags[par][threadIdx.x][q];
+            long long spins = 0;
+            while (*f != seq) {
+                if (++spins > P2P_SPIN_LIMIT) { atomicAdd(&mine->timeouts, 1u); s_dead = 1; break; }
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+        if (s_dead) {                        // never hand out a merge of stale items
+            for (int t = threadIdx.x; t < k; t += blockDim.x) { out_ids[slot + t] = -1; out_scores[slot + t] = -INFINITY; }
+            __syncthreads();
+            continue;
+        }
+        const int total = world * k;
+        int P = 32;
+        while (P < total) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            GatherItem it;
+            if (i < total) {
+                const int r = i / k, t = i - r * k;
+                const volatile GatherItem* src = &mine->items[par][r][slot + t];
+                it.s = src->s;
+                it.id = src->id;
+                if (it.id == -1 && it.s == -INFINITY) it.id = INT64_MAX;
+            } else { it.s = -INFINITY; it.id = INT64_MAX; }
+            sm[i] = it;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= P; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const bool desc = (i & k2) == 0;
+                        const GatherItem a = sm[i], b = sm[ixj];
+                        if (desc ? item_better(b, a) : item_better(a, b)) { sm[i] = b; sm[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int t = threadIdx.x; t < k; t += blockDim.x) {
+            const GatherItem it = sm[t];
+            const bool pad = it.id == INT64_MAX && it.s == -INFINITY;
+            out_ids[slot + t] = pad ? -1 : it.id;
+            out_scores[slot + t] = pad ? -INFINITY : (float)it.s;
+        }
+        __syncthreads();
+    }
+}
+
+// Query all-gather over peer memory: rank r copied ITS contiguous slice of the query batch host -> device into its
+// own region (1/world of the H2D bytes), this kernel pushes the slice to every peer, publishes one flag per CTA,
+// and waits until every rank's slice has landed here.  The search that follows on the stream reads the whole batch
+// from the local region.
+__global__ void __launch_bounds__(256) p2p_query_allgather_kernel(P2PPeers peers, int rank, int world, unsigned int seq,
+                                                                  size_t lo4, size_t hi4 /* my slice, in float4 units */) {
+    const int par = seq & 1;
+    const float4* src = reinterpret_cast<const float4*>(peers.r[rank]->qbuf[par]);
+    for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        for (int r = 0; r < world; ++r)
+            if (r != rank) reinterpret_cast<float4*>(peers.r[r]->qbuf[par])[i] = v;
     }
     __threadfence_system();
     __syncthreads();
-    // 2. publish
     if (threadIdx.x < world) {
-        volatile unsigned int* f = &peers.r[threadIdx.x]->flags[par][rank][q];
+        volatile unsigned int* f = &peers.r[threadIdx.x]->qflags[par][rank][blockIdx.x];
         *f = seq;
     }
-    // 3. wait for every rank's items of this query in MY region (bounded spin: a missing peer must not hang the GPU)
     P2PRegion* mine = peers.r[rank];
-    if (threadIdx.x < world) {
-        volatile unsigned int* f = &mine->flags[par][threadIdx.x][q];
+    // every CTA waits for a share of the (source rank, source CTA) flags; the kernel ends when all have been seen
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < world * (int)gridDim.x; i += gridDim.x * blockDim.x) {
+        volatile unsigned int* f = &mine->qflags[par][i / gridDim.x][i % gridDim.x];
         long long spins = 0;
         while (*f != seq) {
-            if (++spins > (1ll << 28)) { atomicAdd(&mine->timeouts, 1u); break; }
+            if (++spins > P2P_SPIN_LIMIT) { atomicAdd(&mine->timeouts, 1u); break; }
         }
     }
-    __syncthreads();
     __threadfence_system();
-    // 4. merge
-    const int total = world * k;
-    int P = 32;
-    while (P < total) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        GatherItem it;
-        if (i < total) {
-            const int r = i / k, t = i - r * k;
-            const volatile GatherItem* src = &mine->items[par][r][slot + t];
-            it.s = src->s;
-            it.id = src->id;
-            if (it.id == -1 && it.s == -INFINITY) it.id = INT64_MAX;
-        } else { it.s = -INFINITY; it.id = INT64_MAX; }
-        sm[i] = it;
-    }
-    __syncthreads();
-    for (int k2 = 2; k2 <= P; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool desc = (i & k2) == 0;
-                    const GatherItem a = sm[i], b = sm[ixj];
-                    if (desc ? item_better(b, a) : item_better(a, b)) { sm[i] = b; sm[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int t = threadIdx.x; t < k; t += blockDim.x) {
-        const GatherItem it = sm[t];
-        const bool pad = it.id == INT64_MAX && it.s == -INFINITY;
-        out_ids[slot + t] = pad ? -1 : it.id;
-        out_scores[slot + t] = pad ? -INFINITY : (float)it.s;
-    }
 }
 
 static void p2p_free(avs_store* s) {
@@ -209,6 +265,8 @@ static void p2p_free(avs_store* s) {
     for (int r = 0; r < P2P_MAX_WORLD; ++r)
         if (st->peers.r[r] && st->peers.r[r] != st->local) cudaIpcCloseMemHandle(st->peers.r[r]);
     if (st->local) cudaFree(st->local);
+    if (st->h_timeouts) cudaFreeHost(st->h_timeouts);
+    for (cudaEvent_t e : st->tev) cudaEventDestroy(e);
     cudaGetLastError();
     delete st;
     s->p2p_state = nullptr;
@@ -225,6 +283,26 @@ int avs_p2p_timeouts(avs_store* s, int64_t* out) {
     return AVS_OK;
 }
 
+// mean duration (microseconds) of the exchange kernels launched while the scan timing hook was on; -1 if none
+int avs_p2p_exchange_us(avs_store* s, int64_t* out) {
+    P2PState* st = (P2PState*)s->p2p_state;
+    *out = -1;
+    if (!st || st->tev_used == 0) return AVS_OK;
+    double tot = 0.0;
+    for (size_t i = 0; i < st->tev_used; ++i) {
+        AVS_CUDA(cudaEventSynchronize(st->tev[2 * i + 1]));
+        float ms = 0.f;
+        AVS_CUDA(cudaEventElapsedTime(&ms, st->tev[2 * i], st->tev[2 * i + 1]));
+        tot += ms;
+    }
+    *out = (int64_t)(tot / (double)st->tev_used * 1000.0 + 0.5);
+    return AVS_OK;
+}
+void avs_p2p_timing_reset(avs_store* s) {
+    P2PState* st = (P2PState*)s->p2p_state;
+    if (st) st->tev_used = 0;
+}
+
 extern "C" int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out) {
     if (!s || !handle64_out || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) { avs_set_error("avs_p2p_init: bad arguments (rank %d, world %d, max world %d)", rank, world, P2P_MAX_WORLD); return AVS_E_INVALID; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
@@ -238,6 +316,15 @@ extern "C" int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_ou
         return AVS_E_NOMEM;
     }
     AVS_CUDA(cudaMemset(st->local, 0, sizeof(P2PRegion)));
+    AVS_CUDA(cudaDeviceSynchronize());
+    if (cudaHostAlloc((void**)&st->h_timeouts, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) *st->h_timeouts = 0;
+    else { cudaGetLastError(); st->h_timeouts = nullptr; }
+    // the exchange kernel's grid must be co-resident (its CTAs wait for peers' CTAs, never for local ones that are
+    // not running yet): largest item list = 8 ranks x 256 hits -> 2048 x 16 B of dynamic shared memory
+    int per_sm = 0;
+    AVS_CUDA(cudaFuncSetAttribute(p2p_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int)sizeof(GatherItem)));
+    AVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2p_exchange_merge_kernel, 256, 2048 * sizeof(GatherItem)));
+    st->max_ctas = (per_sm < 1 ? 1 : per_sm) * s->num_sms;
     cudaIpcMemHandle_t h;
     AVS_CUDA(cudaIpcGetMemHandle(&h, st->local));
     memcpy(handle64_out, &h, sizeof(h));
@@ -301,27 +388,45 @@ void avs_comm_free(avs_store* s) {
     s->rank = 0;
 }
 
-extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
-                                  void* stream) {
-    if (!s) { avs_set_error("avs_search_sharded: NULL store"); return AVS_E_INVALID; }
-    P2PState* p2p = (P2PState*)s->p2p_state;
-    const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
-    if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
-    if (s->filter) { avs_set_error("avs_search_sharded: row filters are not supported on a sharded store"); return AVS_E_STATE; }
-    cudaStream_t st = (cudaStream_t)stream;
-    // local exact top-k; ids/scores land in the caller's buffers first and are then replaced
-    AVS_CHECK(avs_search_local(s, q, nq, k, out_ids, out_scores, nullptr, st));
-    if (nq == 0) return AVS_OK;
+// A peer that stopped answering poisoned the affected queries on the device; the pinned mirror of the counter tells the
+// host without a synchronisation.  From then on the call fails loudly and the store falls back to the NCCL exchange.
+static int p2p_check_health(avs_store* s, P2PState* p2p) {
+    if (!p2p || !p2p->h_timeouts) return AVS_OK;
+    const unsigned int now = *(volatile unsigned int*)p2p->h_timeouts;
+    if (now != p2p->seen_timeouts) {
+        p2p->seen_timeouts = now;
+        s->opt_p2p = 0;
+        avs_set_error("peer-memory exchange timed out %u time(s): a rank stopped answering; the affected queries were returned "
+                      "as id -1 / -inf and this store now uses the NCCL exchange", now);
+        return AVS_E_NCCL;
+    }
+    return AVS_OK;
+}
+
+static int exchange_and_merge(avs_store* s, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st, bool use_p2p) {
     AvsScratch& c = s->sc;
+    P2PState* p2p = (P2PState*)s->p2p_state;
     if (use_p2p) {
         int P = 32;
         while (P < s->world * k) P <<= 1;
         p2p->seq += 1;
         if (p2p->seq == 0) p2p->seq = 2;   // 0 is the "never written" value of the flags; keep the parity sequence
-        p2p_exchange_merge_kernel<<<nq, 256, (size_t)P * sizeof(GatherItem), st>>>(p2p->peers, s->rank, s->world, p2p->seq, nq, k,
-                                                                                 c.out_s64, out_ids, out_scores);
+        const int grid = nq < p2p->max_ctas ? nq : p2p->max_ctas;
+        const bool timed = s->timing && p2p->tev_used < 4096;
+        if (timed) {
+            if (2 * p2p->tev_used >= p2p->tev.size()) {
+                cudaEvent_t a, b;
+                AVS_CUDA(cudaEventCreate(&a)); AVS_CUDA(cudaEventCreate(&b));
+                p2p->tev.push_back(a); p2p->tev.push_back(b);
+            }
+            AVS_CUDA(cudaEventRecord(p2p->tev[2 * p2p->tev_used], st));
+        }
+        p2p_exchange_merge_kernel<<<grid, 256, (size_t)P * sizeof(GatherItem), st>>>(p2p->peers, s->rank, s->world, p2p->seq, nq, k,
+                                                                                   c.out_s64, out_ids, out_scores);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
+        if (timed) { AVS_CUDA(cudaEventRecord(p2p->tev[2 * p2p->tev_used + 1], st)); p2p->tev_used++; }
+        if (p2p->h_timeouts) AVS_CUDA(cudaMemcpyAsync(p2p->h_timeouts, &p2p->local->timeouts, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         return AVS_OK;
     }
     const size_t items = (size_t)nq * k;
@@ -348,5 +453,82 @@ extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, i
     shard_merge_kernel<<<nq, 256, (size_t)P * sizeof(GatherItem), st>>>((const GatherItem*)c.gather_recv, s->world, nq, k, out_ids, out_scores);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
+    return AVS_OK;
+}
+
+extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
+                                  void* stream) {
+    if (!s) { avs_set_error("avs_search_sharded: NULL store"); return AVS_E_INVALID; }
+    P2PState* p2p = (P2PState*)s->p2p_state;
+    AVS_CHECK(p2p_check_health(s, p2p));
+    const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
+    if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
+    if (s->filter) { avs_set_error("avs_search_sharded: row filters are not supported on a sharded store"); return AVS_E_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // local exact top-k; ids/scores land in the caller's buffers first and are then replaced
+    AVS_CHECK(avs_search_local(s, q, nq, k, out_ids, out_scores, nullptr, st));
+    if (nq == 0) return AVS_OK;
+    return exchange_and_merge(s, nq, k, out_ids, out_scores, st, use_p2p);
+}
+
+// End to end from HOST buffers on a sharded store.  Every rank holds the same host query batch; with the peer regions
+// connected each rank copies only ITS 1/world slice host -> device and the slices are all-gathered over NVLink by
+// p2p_query_allgather_kernel (one PCIe copy of the batch per node instead of `world`); otherwise every rank copies the
+// whole batch.  Local search, exchange + merge, one D2H copy of the merged hits, synchronised on return.
+extern "C" int avs_search_sharded_host(avs_store* s, const float* q_host, int nq, int k, int64_t* out_ids_host,
+                                       float* out_scores_host) {
+    if (!s) { avs_set_error("avs_search_sharded_host: NULL store"); return AVS_E_INVALID; }
+    if (nq < 0 || (nq > 0 && (!q_host || !out_ids_host || !out_scores_host))) { avs_set_error("avs_search_sharded_host: NULL buffer"); return AVS_E_INVALID; }
+    if (nq == 0) return AVS_OK;
+    P2PState* p2p = (P2PState*)s->p2p_state;
+    AVS_CHECK(p2p_check_health(s, p2p));
+    const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
+    if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded_host: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
+    if (s->filter) { avs_set_error("avs_search_sharded_host: row filters are not supported on a sharded store"); return AVS_E_STATE; }
+    AVS_CUDA(cudaSetDevice(s->device));
+    AVS_CHECK(avs_host_staging_reserve(s, nq, k));
+    AvsScratch& c = s->sc;
+    cudaStream_t st = 0;
+    const size_t items = (size_t)nq * k;
+    int64_t* d_ids = c.d_ids;
+    float* d_scores = reinterpret_cast<float*>(c.d_ids + 2 * items);
+    const size_t total_f = (size_t)nq * s->dim;
+    const float* q_dev = c.h2d_q;
+    // queries leave from the caller's buffer when it is pinned, else through the pinned stage (only the bytes this rank copies)
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, q_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const bool gather_q = use_p2p && s->world > 1 && (s->dim % 4 == 0) && total_f <= P2P_Q_FLOATS && nq >= s->world;
+    if (gather_q) {
+        p2p->qseq += 1;
+        if (p2p->qseq == 0) p2p->qseq = 2;
+        const int par = p2p->qseq & 1;
+        const int per = (nq + s->world - 1) / s->world;
+        const int lo = s->rank * per < nq ? s->rank * per : nq, hi = lo + per < nq ? lo + per : nq;
+        float* qbuf = p2p->local->qbuf[par];
+        if (hi > lo) {
+            const size_t off = (size_t)lo * s->dim, nb = (size_t)(hi - lo) * s->dim * sizeof(float);
+            const float* src = q_host + off;
+            if (!pinned) { memcpy(c.h_q + off, q_host + off, nb); src = c.h_q + off; }
+            AVS_CUDA(cudaMemcpyAsync(qbuf + off, src, nb, cudaMemcpyHostToDevice, st));
+        }
+        p2p_query_allgather_kernel<<<P2P_Q_CTAS, 256, 0, st>>>(p2p->peers, s->rank, s->world, p2p->qseq,
+                                                               (size_t)lo * s->dim / 4, (size_t)hi * s->dim / 4);
+        s->st_launches++;
+        AVS_CUDA(cudaGetLastError());
+        q_dev = qbuf;
+    } else {
+        const float* src = q_host;
+        if (!pinned) { memcpy(c.h_q, q_host, total_f * sizeof(float)); src = c.h_q; }
+        AVS_CUDA(cudaMemcpyAsync(c.h2d_q, src, total_f * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    AVS_CHECK(avs_search_local(s, q_dev, nq, k, d_ids, d_scores, nullptr, st));
+    AVS_CHECK(exchange_and_merge(s, nq, k, d_ids, d_scores, st, use_p2p));
+    AVS_CUDA(cudaMemcpyAsync(c.h_out, d_ids, items * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AVS_CUDA(cudaMemcpyAsync(c.h_out + 2 * items, d_scores, items * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AVS_CUDA(cudaStreamSynchronize(st));
+    AVS_CHECK(p2p_check_health(s, p2p));
+    memcpy(out_ids_host, c.h_out, items * sizeof(int64_t));
+    memcpy(out_scores_host, c.h_out + 2 * items, items * sizeof(float));
     return AVS_OK;
 }

@@ -868,6 +868,7 @@ extern "C" int avs_scan_timing(avs_store* s, int enable_reset, double* mean_ms, 
     if (enable_reset >= 0) {
         s->timing = enable_reset != 0;
         s->tev_used = 0;
+        avs_p2p_timing_reset(s);
     }
     return AVS_OK;
 }
@@ -984,6 +985,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : ((use_gemm || hybrid) ? s->opt_coarse_sigma : 8)) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
+            if (j > 256) j = 256;            // the radix select hands at most 256 survivors to the next level
             j_ranks[i] = (int)j;
             need = 1.5 * (double)j + 16.0;
         }
@@ -1066,6 +1068,29 @@ extern "C" int avs_search(avs_store* s, const float* q, int nq, int k, int64_t* 
     return avs_search_local(s, q, nq, k, out_ids, out_scores, out_rows, (cudaStream_t)stream);
 }
 
+// one device block [ids | rows | scores] and one pinned host mirror: a single D2H copy brings every result back
+int avs_host_staging_reserve(avs_store* s, int nq, int k) {
+    AvsScratch& c = s->sc;
+    if (nq <= c.host_nq_cap && k <= c.host_k_cap) return AVS_OK;
+    AVS_CUDA(cudaDeviceSynchronize());
+    const int nq2 = nq > c.host_nq_cap ? nq : c.host_nq_cap, k2 = k > c.host_k_cap ? k : c.host_k_cap;
+    const size_t cap_items = (size_t)nq2 * k2;
+    AVS_CHECK(dev_alloc(&c.h2d_q, (size_t)nq2 * s->dim));
+    AVS_CHECK(dev_alloc(&c.d_ids, cap_items * 3));                 // ids, rows (int64) and scores (fp32, 8-byte slots)
+    if (c.h_out) cudaFreeHost(c.h_out);
+    if (c.h_q) cudaFreeHost(c.h_q);
+    c.h_out = nullptr; c.h_q = nullptr;
+    c.host_nq_cap = c.host_k_cap = 0;
+    if (cudaHostAlloc((void**)&c.h_out, cap_items * 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&c.h_q, (size_t)nq2 * s->dim * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        avs_set_error("out of pinned host memory for the search staging buffers");
+        return AVS_E_NOMEM;
+    }
+    c.host_nq_cap = nq2; c.host_k_cap = k2;
+    return AVS_OK;
+}
+
 extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k, int64_t* out_ids_host,
                                float* out_scores_host, int64_t* out_rows_host) {
     if (!s) { avs_set_error("avs_search_host: NULL store"); return AVS_E_INVALID; }
@@ -1073,26 +1098,9 @@ extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k,
     if (k < 1 || k > AVS_MAX_KPRIME) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
     if (nq == 0) return AVS_OK;
     AVS_CUDA(cudaSetDevice(s->device));
+    AVS_CHECK(avs_host_staging_reserve(s, nq, k));
     AvsScratch& c = s->sc;
-    // one device block [ids | rows | scores] and one pinned host mirror: a single D2H copy brings every result back
     const size_t items = (size_t)nq * k;
-    if (nq > c.host_nq_cap || k > c.host_k_cap) {
-        AVS_CUDA(cudaDeviceSynchronize());
-        const int nq2 = nq > c.host_nq_cap ? nq : c.host_nq_cap, k2 = k > c.host_k_cap ? k : c.host_k_cap;
-        const size_t cap_items = (size_t)nq2 * k2;
-        AVS_CHECK(dev_alloc(&c.h2d_q, (size_t)nq2 * s->dim));
-        AVS_CHECK(dev_alloc(&c.d_ids, cap_items * 3));                 // ids, rows (int64) and scores (fp32, 8-byte slots)
-        if (c.h_out) cudaFreeHost(c.h_out);
-        if (c.h_q) cudaFreeHost(c.h_q);
-        c.h_out = nullptr; c.h_q = nullptr;
-        if (cudaHostAlloc((void**)&c.h_out, cap_items * 3 * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc((void**)&c.h_q, (size_t)nq2 * s->dim * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            avs_set_error("out of pinned host memory for the search staging buffers");
-            return AVS_E_NOMEM;
-        }
-        c.host_nq_cap = nq2; c.host_k_cap = k2;
-    }
     int64_t* d_ids = c.d_ids;
     int64_t* d_rows = c.d_ids + items;
     float* d_scores = reinterpret_cast<float*>(c.d_ids + 2 * items);
@@ -1149,6 +1157,7 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "last_levels") *out = s->st_last_levels;
     else if (k == "last_final_rows") *out = s->st_last_final_rows;
     else if (k == "p2p_timeouts") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_timeouts(s, out); }
+    else if (k == "exchange_us") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_exchange_us(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k == "last_uncertified") *out = s->st_last_uncertified;   // of the last avs_search_host call; no device sync
     else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries") {

@@ -226,6 +226,10 @@ static int alloc_arrays(avs_store* s, int64_t cap, float** master, __nv_bfloat16
     // padding rows of the bf16 copy must be zero: tiles are always whole groups
     AVS_CUDA(cudaMemset(*xb, 0, bx));
     AVS_CUDA(cudaMemset(*inv, 0, (size_t)cap * sizeof(float)));
+    // the memsets run on the legacy default stream and are asynchronous to the host for device memory; the rows
+    // that follow are written on the caller's stream, which may be non-blocking (every non-default torch stream
+    // is): finish the clears before anything can be ordered against them
+    AVS_CUDA(cudaDeviceSynchronize());
     return AVS_OK;
 }
 
@@ -298,6 +302,7 @@ extern "C" int avs_reserve(avs_store* s, int64_t capacity) {
     AVS_CUDA(cudaMemcpy(x, s->xb, (size_t)s->count * s->dpad * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
     AVS_CUDA(cudaMemcpy(inv, s->inv_norm, (size_t)s->count * sizeof(float), cudaMemcpyDeviceToDevice));
     AVS_CUDA(cudaMemcpy(ids, s->ids, (size_t)s->count * sizeof(int64_t), cudaMemcpyDeviceToDevice));
+    AVS_CUDA(cudaDeviceSynchronize());   // device-to-device copies return before they ran (see alloc_arrays)
     cudaFree(s->master); cudaFree(s->xb); cudaFree(s->inv_norm); cudaFree(s->ids);
     s->master = m; s->xb = x; s->inv_norm = inv; s->ids = ids;
     s->capacity = cap;
@@ -391,13 +396,17 @@ extern "C" int avs_set_filter(avs_store* s, const uint32_t* bitmap_host, int64_t
     }
     if (n_bits != s->count) { avs_set_error("avs_set_filter: bitmap has %lld bits, the store %lld rows", (long long)n_bits, (long long)s->count); return AVS_E_INVALID; }
     const size_t words = (size_t)((n_bits + 31) / 32);
+    // the tensor-core scan reads one bitmap word per 32-row chunk of WHOLE 256-row groups (padding chunks of the last
+    // group included, masked afterwards): the allocation covers whole groups and the tail words are zero
+    const size_t words_alloc = (size_t)(round_up(n_bits > 0 ? n_bits : 1, AVS_GROUP_ROWS) / 32);
     AVS_CUDA(cudaDeviceSynchronize());
-    if (words > s->filter_words || !s->filter) {
+    if (words_alloc > s->filter_words || !s->filter) {
         cudaFree(s->filter);
         s->filter = nullptr;
-        if (cudaMalloc((void**)&s->filter, (words ? words : 1) * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->filter_words = 0; avs_set_error("out of device memory for the filter bitmap"); return AVS_E_NOMEM; }
-        s->filter_words = words ? words : 1;
+        if (cudaMalloc((void**)&s->filter, words_alloc * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); s->filter_words = 0; avs_set_error("out of device memory for the filter bitmap"); return AVS_E_NOMEM; }
+        s->filter_words = words_alloc;
     }
+    AVS_CUDA(cudaMemset(s->filter, 0, s->filter_words * sizeof(uint32_t)));
     int64_t allowed = 0;
     for (size_t w = 0; w < words; ++w) {
         uint32_t v = bitmap_host[w];
@@ -405,6 +414,7 @@ extern "C" int avs_set_filter(avs_store* s, const uint32_t* bitmap_host, int64_t
         allowed += __builtin_popcount(v);
     }
     AVS_CUDA(cudaMemcpy(s->filter, bitmap_host, words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    AVS_CUDA(cudaDeviceSynchronize());
     s->filter_allowed = allowed;
     return AVS_OK;
 }

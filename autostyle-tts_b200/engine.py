@@ -26,7 +26,7 @@ METRIC_NAMES = {0: "COSINE", 1: "IP"}
 ABI_SYMBOLS = (
     "avs_create", "avs_destroy", "avs_reserve", "avs_insert", "avs_fill_synthetic", "avs_count", "avs_dim",
     "avs_metric", "avs_get_rows", "avs_get_ids", "avs_set_filter", "avs_search", "avs_search_host", "avs_nccl_unique_id",
-    "avs_comm_init", "avs_search_sharded", "avs_p2p_init", "avs_p2p_connect", "avs_set_option", "avs_get_stat", "avs_scan_timing",
+    "avs_comm_init", "avs_search_sharded", "avs_search_sharded_host", "avs_p2p_init", "avs_p2p_connect", "avs_set_option", "avs_get_stat", "avs_scan_timing",
     "avs_last_error", "avs_version",
 )
 
@@ -76,6 +76,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "avs_nccl_unique_id": (i32, [vp]),
         "avs_comm_init": (i32, [vp, vp, i32, i32]),
         "avs_search_sharded": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+        "avs_search_sharded_host": (i32, [vp, vp, i32, i32, vp, vp]),
         "avs_p2p_init": (i32, [vp, i32, i32, vp]),
         "avs_p2p_connect": (i32, [vp, vp, i32]),
         "avs_set_option": (i32, [vp, ctypes.c_char_p, i64]),
@@ -166,6 +167,14 @@ class Store:
         _check(self._lib, self._lib.avs_get_rows(self._h, int(first), int(n), out.ctypes.data, None))
         return out
 
+    def get_rows_device(self, first: int, n: int):
+        """Master rows [first, first+n) as a torch CUDA tensor on the store's device (device-to-device copy)."""
+        torch = _torch()
+        out = torch.empty((int(n), self.dim), dtype=torch.float32, device=torch.device("cuda", self.device))
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        _check(self._lib, self._lib.avs_get_rows(self._h, int(first), int(n), out.data_ptr(), stream or None))
+        return out
+
     def get_ids(self, first: int, n: int) -> np.ndarray:
         out = np.empty(int(n), dtype=np.int64)
         _check(self._lib, self._lib.avs_get_ids(self._h, int(first), int(n), out.ctypes.data, None))
@@ -199,14 +208,15 @@ class Store:
                 _check(self._lib, self._lib.avs_search(self._h, q.data_ptr(), nq, int(k), ids.data_ptr(), sc.data_ptr(),
                                                        rows.data_ptr() if rows is not None else None, stream or None))
             return (ids, sc, rows) if return_rows else (ids, sc)
-        if sharded:
-            raise AvsError(-1, "sharded search takes device tensors")
         if torch is not None and isinstance(queries, torch.Tensor):
             queries = queries.detach().cpu().numpy()
         q = _as_f32_matrix(queries, self.dim, "search")
         nq = q.shape[0]
         ids = np.empty((nq, k), dtype=np.int64)
         sc = np.empty((nq, k), dtype=np.float32)
+        if sharded:
+            _check(self._lib, self._lib.avs_search_sharded_host(self._h, q.ctypes.data, nq, int(k), ids.ctypes.data, sc.ctypes.data))
+            return ids, sc
         rows = np.empty((nq, k), dtype=np.int64)
         _check(self._lib, self._lib.avs_search_host(self._h, q.ctypes.data, nq, int(k), ids.ctypes.data, sc.ctypes.data,
                                                     rows.ctypes.data))

@@ -77,6 +77,8 @@ class ShardedStore:
         self.store.insert(rows, ids)
 
     def search(self, queries, k: int):
+        """Device tensor in -> device tensors out (asynchronous); host array in -> numpy out, end to end
+        (`avs_search_sharded_host`: each rank copies 1/world of the batch H2D, NVLink all-gather, search, merge, D2H)."""
         if self.world == 1:
             return self.store.search(queries, k)
         return self.store.search(queries, k, sharded=True)

@@ -110,6 +110,13 @@ int avs_comm_init(avs_store* s, const void* unique_id128, int rank, int world);
  * id i64) -> merge by (score desc, id asc); every rank receives the global result. */
 int avs_search_sharded(avs_store* s, const float* q, int nq, int k,
                        int64_t* out_ids, float* out_scores, void* stream);
+/* Same sharded search end to end from HOST buffers (every rank passes the same batch): with the peer regions connected
+ * each rank copies only its 1/world slice of the queries host -> device and the slices are all-gathered over NVLink
+ * peer memory; local search, exchange + merge, D2H of the merged hits; synchronised on return.  This is what the
+ * reference's per-utterance `client.search(data=[emb])` loop (/root/reference/milvus/search_json.py:382-411) becomes on a
+ * row-sharded store. */
+int avs_search_sharded_host(avs_store* s, const float* q_host, int nq, int k,
+                            int64_t* out_ids_host, float* out_scores_host);
 /* Optional fused exchange over NVLink peer memory (replaces the ncclAllGather + merge of
  * avs_search_sharded by ONE kernel that stores each rank's top-k straight into its peers' memory, flags
  * it, waits for the peers' items and merges).  avs_p2p_init allocates this rank's exchange region and
@@ -127,7 +134,8 @@ int avs_p2p_connect(avs_store* s, const void* handles, int world);
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
- * "uncertified_queries", "p2p_timeouts", "last_kprime", "last_levels", "last_scan_path", "last_final_rows";
+ * "uncertified_queries", "p2p_timeouts", "exchange_us" (mean duration of the peer-memory exchange kernel while
+ * avs_scan_timing is on), "last_kprime", "last_levels", "last_scan_path", "last_final_rows";
  * "last_uncertified": queries of the last avs_search_host call whose top-k could not be proven exact (more than 4096
  * rows tied with the k-th score) - read without a device synchronisation. */
 int avs_get_stat(avs_store* s, const char* key, int64_t* out);

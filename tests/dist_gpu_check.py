@@ -49,10 +49,17 @@ def main():
             good = np.array_equal(ids, exp_ids) and np.all(np.abs(sc - exp_d) <= 1e-5 * np.maximum(1, np.abs(exp_d)))
             if not good:
                 flag.zero_()
+        # end to end from host buffers: 1/world of the batch copied per rank, NVLink all-gather of the slices, search, merge
+        ss.store.set_option("p2p_merge", 1 if ss.p2p else 0)
+        for rep in range(3):
+            h_ids, h_sc = ss.search(Q, k)
+        good = np.array_equal(h_ids, exp_ids) and np.all(np.abs(h_sc - exp_d) <= 1e-5 * np.maximum(1, np.abs(exp_d)))
+        if not good:
+            flag.zero_()
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(f"world={world} n={n} d={d} nq={nq} k={k} {metric}: {'OK' if flag.item() else 'MISMATCH'} "
-                  f"(modes {[m[0] for m in modes]}, shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
+                  f"(modes {[m[0] for m in modes] + ['host']}, shard rows {len(ss.store)}, path {ss.store.stat('last_scan_path')}, "
                   f"uncertified {ss.store.stat('uncertified_queries')}, p2p timeouts {ss.store.stat('p2p_timeouts')})", flush=True)
         ok &= bool(flag.item())
         ss.close()

@@ -196,6 +196,31 @@ def test_filter_expression_compiler():
             fe.compile_filter(bad)
 
 
+def test_filter_literals_are_never_rewritten_and_arithmetic_is_numeric_only():
+    """keywords inside string literals (`AND`, `true`, `IN`, `$meta`, `&&`) must reach the comparison verbatim,
+    and `"x" * 4000000000` must be a type error (row false), not a multi-GB allocation."""
+    fe = load_pkg("filter_expr")
+    pkg = load_pkg()
+    rows = [{"id": 1, "speaker": "Tom AND Jerry", "text": "this is true", "tag": "IN", "n": 7},
+            {"id": 2, "speaker": "tom and jerry", "text": "a && b || !c", "tag": "$meta", "n": -7},
+            {"id": 3, "speaker": "LIKE", "text": "50%", "tag": "not", "n": 2}]
+    cases = {'speaker == "Tom AND Jerry"': [True, False, False], 'text == "this is true"': [True, False, False],
+             'tag in ["IN"]': [True, False, False], 'tag == "$meta" OR tag == "not"': [False, True, True],
+             'text == "a && b || !c"': [False, True, False], 'speaker == "LIKE" and text like "50%"': [False, False, True],
+             "speaker == 'tom and jerry' AND NOT (id IN [1, 3])": [False, True, False],
+             '"x" * 4000000000 == "y"': [False, False, False], 'speaker * 4000000000 == "y"': [False, False, False],
+             "n / 2 == 3": [True, False, False], "n / 2 == -3": [False, True, False],     # int64 division truncates toward zero
+             "n * 1000000000 * 1000000000 * 1000000000 > 0": [True, False, True],
+             '$meta["tag"] like "%meta"': [False, True, False]}
+    for expr, want in cases.items():
+        pred = fe.compile_filter(expr)
+        assert [pred(r) for r in rows] == want, expr
+        assert pred.rows(rows, "id", [r["id"] for r in rows]) == want, expr
+    for bad in ['speaker == "unterminated', "__lit_0__ == 1", "id ** 2 == 4", "x" * 70000]:
+        with pytest.raises(pkg.MilvusException):
+            fe.compile_filter(bad)
+
+
 def test_hot_kernels_stay_lean_and_blackwell_native(pkg):
     """Regression guard measured the hard way: the tensor-core scan is instruction-cache and register sensitive
     (a 10.8 k-instruction build with spills ran 35 % slower).  Also proves the SASS is tcgen05 / TMA / TMEM."""
