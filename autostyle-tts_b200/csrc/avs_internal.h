@@ -15,8 +15,7 @@ typedef unsigned long long u64;
 
 #define AVS_GROUP_ROWS 256      // sampling / tiling granularity of the scan (rows)
 #define AVS_MAX_KPRIME 256      // largest oversampled candidate list
-#define AVS_REPAIR_CAP 4096     // exact-repair collection buffer per flagged query
-#define AVS_MAX_REPAIR_Q 256    // flagged queries repaired per search
+#define AVS_REPAIR_CAP 4096     // largest exact-repair slice per flagged query (rows tied at the k-th score beyond it: uncertified)
 #define AVS_MAX_LEVELS 12
 #define AVS_DENSE_CAP 65536      // rows of the threshold-free level of the gemv path (dense key buffer per query)
 #define AVS_DENSE_MAX_NQ 64      // the dense buffer is kept for this many queries
@@ -86,6 +85,21 @@ __host__ __device__ __forceinline__ int64_t avs_level_group(const AvsLevel& lv, 
     return j * lv.stride;
 }
 
+// Everything the persistent tensor-core scan needs for one search: the levels it scans in ONE launch and what the
+// fused warp-per-query selects between them need (select_warp.cuh).
+struct AvsScanPlan {
+    int n_levels;                       // levels scanned by this launch
+    int last_is_final;                  // its last level is the final level of the search (select -> top K' + bound)
+    int nq, kprime, cap;
+    int64_t n_eff;                      // rows that may be returned (filter-allowed count)
+    AvsLevel lv[AVS_MAX_LEVELS];
+    int j_rank[AVS_MAX_LEVELS];
+    int k_eps[AVS_MAX_LEVELS];          // > 0 on the level whose select sets the LAST threshold under the eps rule
+    u64* tau; u64* cand; int* cnt; u64* topkeys; int* topn; float* bound; int* status; const float* eps;
+    unsigned int* gbar;                 // grid barrier counter (zeroed by prep_queries_kernel)
+    unsigned int* err;                  // bumped when a bounded barrier spin gives up
+};
+
 struct AvsScratch {
     // query preparation
     float* qf = nullptr;          // [nq_pad, dpad] fp32, normalised for COSINE, zero padded
@@ -104,11 +118,15 @@ struct AvsScratch {
     double* out_s64 = nullptr;    // [nq, k] exact scores of the final hits (for the shard merge)
     // repair
     int* flagged = nullptr;       // [1 + nq] stage 1 (wide rescoring): count, then query indices
-    int* flagged2 = nullptr;      // [1 + AVS_MAX_REPAIR_Q] stage 2 (exact scan): count, then query indices
-    double* rep_s = nullptr;      // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
-    uint32_t* rep_row = nullptr;  // [AVS_MAX_REPAIR_Q, AVS_REPAIR_CAP]
-    int* rep_cnt = nullptr;       // [AVS_MAX_REPAIR_Q]
-    double* rep_thr = nullptr;    // [AVS_MAX_REPAIR_Q]
+    int* flagged2 = nullptr;      // [1 + nq] stage 2 (exact scan): count, then query indices
+    unsigned int* gbar = nullptr; // [4] grid-barrier counters of the persistent kernels (scan, repair), zeroed by prep
+    double* rep_s = nullptr;      // [pool_items] exact-repair pool: scores ...
+    uint32_t* rep_row = nullptr;  // [pool_items] ... and rows, cut into one slice per flagged query
+    int* rep_cnt = nullptr;       // [nq] rows collected per flagged query
+    double* rep_thr = nullptr;    // [nq] lower bound of the k-th best exact score per flagged query (-inf: none)
+    int* rep_sel = nullptr;       // [nq, 2] threshold search: histogram bin of the k-th best, rows above it
+    unsigned int* rep_hist = nullptr;  // [8, 4096] histogram of the threshold search
+    size_t pool_items = 0;
     // sharded search
     void* gather_send = nullptr;  // [nq, k] (f64 score, i64 id)
     void* gather_recv = nullptr;  // [world, nq, k]
@@ -142,11 +160,12 @@ struct avs_store {
     int64_t st_last_uncertified = 0;           // queries of the last avs_search_host call whose top-k could not be proven
     unsigned long long* h_stats = nullptr;  // pinned host mirror of dstat, refreshed asynchronously after every search
     unsigned long long seen_repaired = 0;
+    size_t rep_smem_seen = 0;         // shared-memory size the repair kernel's occupancy was last queried for
     bool eps_rule = false;            // set once an exact repair was needed: the last threshold then honours eps
     AvsScratch sc;
     int num_sms = 148;
     // options
-    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 3, opt_ratio = 32, opt_force_repair = 0,
+    int opt_scan_path = 0, opt_oversample = 0, opt_gemm_min_batch = 1, opt_ratio = 32, opt_force_repair = 0,
         opt_cta_group = 2;
     // stats
     int64_t st_launches = 0, st_searches = 0, st_queries = 0, st_last_final_rows = 0;
@@ -173,7 +192,7 @@ struct avs_store {
 
 // ---- host entry points implemented across translation units ----------------------------------
 int avs_launch_scan_gemv(avs_store* s, int q0, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
-int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st);
+int avs_launch_scan_gemm(avs_store* s, int nq, const AvsScanPlan& plan, cudaStream_t st);
 void avs_gemm_state_free(avs_store* s);
 int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_ids, float* out_scores,
                      int64_t* out_rows, cudaStream_t st);

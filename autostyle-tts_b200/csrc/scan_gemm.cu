@@ -17,9 +17,18 @@
 // the CTAs (pairs), so the pairs that run side by side sweep the query blocks over the same database
 // tile: one HBM read, the rest from L2.
 // Algorithmic flops per launch: 2 * nq_pad * rows_visited * D_pad.
+//
+// ONE launch scans every level of a search (device-side level loop).  The TMA producer and the MMA issuer run
+// straight through all levels - their tiles do not depend on the thresholds, so the first tiles of level l+1 are
+// already in shared memory / TMEM while level l is being selected.  Only the epilogue warps synchronise:
+//   flush survivors -> grid barrier -> every epilogue warp of the grid selects queries in turn (select_warp.cuh:
+//   rank-j key = next threshold, survivors compacted) -> grid barrier -> next level with the new thresholds.
+// The grid never exceeds what the device keeps resident (one CTA per SM), so the barrier cannot wait for a CTA that
+// has not started; its spin is bounded all the same and a give-up is reported through `err`.
 #include <cuda.h>
 
 #include "avs_internal.h"
+#include "select_warp.cuh"
 
 namespace {
 
@@ -141,11 +150,36 @@ struct PipeState {
     }
 };
 
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// Grid-wide barrier among the epilogue groups of all CTAs; called by every epilogue thread.
+__device__ __forceinline__ void grid_barrier_epi(unsigned int* gbar, unsigned int& epoch, unsigned int* err) {
+    __threadfence();
+    epi_sync();
+    epoch += 1;
+    if (threadIdx.x == 128) {
+        const unsigned int target = epoch * gridDim.x;
+        atomicAdd(gbar, 1u);
+        long long spins = 0;
+        while (ld_acquire_u32(gbar) < target) {
+            __nanosleep(20);
+            if (++spins > (1ll << 22)) { atomicAdd(err, 1u); break; }   // ~2 s: a CTA is missing; results are flagged, the GPU is not hung
+        }
+        __threadfence();
+    }
+    epi_sync();
+}
+
 template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
-                 int64_t n_rows, int n_qblocks, int num_k_blocks, AvsLevel lv, const u64* __restrict__ tau,
-                 u64* __restrict__ cand, int* __restrict__ cnt, int cap, const uint32_t* __restrict__ filt) {
+                 int64_t n_rows, int n_qblocks, int num_k_blocks, const __grid_constant__ AvsScanPlan plan,
+                 const uint32_t* __restrict__ filt) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -159,8 +193,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     u64* stash_smem = tau_smem + TAU_CACHE;
     const int n_tau = n_qblocks * BLOCK_M * CG;
     const bool tau_cached = n_tau <= TAU_CACHE;
-    if (tau_cached)
-        for (int i = threadIdx.x; i < n_tau; i += GEMM_THREADS) tau_smem[i] = tau[i];
+    const u64* __restrict__ tau = plan.tau;
+    u64* __restrict__ cand = plan.cand;
+    int* __restrict__ cnt = plan.cnt;
+    const int cap = plan.cap;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CG == 1 ? 0u : cluster_ctarank();
@@ -168,7 +204,6 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
     // work unit = (visited row group, query block); units are dealt round-robin to the CTAs (pairs), so the
     // CTAs that run side by side sweep the query blocks over the same database tile: one HBM read, L2 re-use
-    const int64_t n_tiles = lv.n_visit * n_qblocks;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -203,8 +238,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== TMA producer (one lane) =====
         if (lane == 0) {
             PipeState ps;
-            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-                {
+            for (int l = 0; l < plan.n_levels; ++l) {
+                const AvsLevel& lv = plan.lv[l];
+                const int64_t n_tiles = lv.n_visit * n_qblocks;
+                for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
                     const int64_t m = t / n_qblocks;
                     const int qb = (int)(t - m * n_qblocks);
                     const int64_t g = avs_level_group(lv, m);
@@ -230,8 +267,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                    ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
             PipeState ps;
             uint32_t acc = 0, acc_phase = 0;
-            for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-                {
+            for (int l = 0; l < plan.n_levels; ++l) {
+                const int64_t n_tiles = plan.lv[l].n_visit * n_qblocks;
+                for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
                     mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -269,6 +307,14 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 if (pend_pos + i < cap) pend_dst[pend_pos + i] = my_stash[i];
             pend_n = 0;
         };
+        unsigned int epoch = 0;
+        for (int l = 0; l < plan.n_levels; ++l) {
+        const AvsLevel& lv = plan.lv[l];
+        const int64_t n_tiles = lv.n_visit * n_qblocks;
+        if (tau_cached) {                              // this level's thresholds (the previous select wrote them)
+            for (int i = threadIdx.x - 128; i < n_tau; i += 256) tau_smem[i] = tau[i];
+            epi_sync();
+        }
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
             const int64_t m = t / n_qblocks;
             const int qb = (int)(t - m * n_qblocks);
@@ -301,7 +347,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     u64* const stage = stash_smem + (size_t)(warp - 4) * 32 * STASH;
                     const int rq = lane >> 3, rc = lane & 7;                       // reader role: query 4j + rq, key rc of the slice
                     u64* const gbase = cand + (size_t)(q - lane) * cap + (size_t)m * BLOCK_N + half * 128 + col0;
-                    const bool live = tau_k != ~0ull;                              // padding query slots keep empty keys
+                    const bool live = q < plan.nq;                                 // padding query slots keep empty keys
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
 #pragma unroll
@@ -399,6 +445,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         flush_pending();
+        // ---- level done on this CTA: wait for the whole grid, then select (warp per query), then the next level ----
+        grid_barrier_epi(plan.gbar, epoch, plan.err);
+        {
+            const bool final_level = plan.last_is_final && l == plan.n_levels - 1;
+            u64* const list = stash_smem + (size_t)(warp - 4) * 256;           // 2 KB of the (now idle) survivor stash per warp
+            const int dense_total = lv.dense ? (int)(lv.n_visit * AVS_GROUP_ROWS) : 0;
+            for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
+                warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);
+        }
+        if (l + 1 < plan.n_levels) grid_barrier_epi(plan.gbar, epoch, plan.err);
+        }
     }
 
     tc_fence_before();
@@ -441,7 +498,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int dpad, int box
 }
 
 template <int CG>
-int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
+int launch(avs_store* s, int nq, const AvsScanPlan& plan, cudaStream_t st) {
     using C = Cfg<CG>;
     const int q_block = BLOCK_M * CG;
     const int nq_pad = (nq + 255) / 256 * 256;            // prep_queries pads to 256: whole blocks for both CG
@@ -450,12 +507,35 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
     AVS_CHECK(make_map(&mq, s->sc.qb, nq_pad, s->dpad, BLOCK_M));
     AVS_CHECK(make_map(&mx, s->xb, s->capacity, s->dpad, C::LOAD_N));
     static bool attr[64] = {};   // function attributes are per device
+    static int max_clusters[64] = {};
     if (!attr[s->device & 63]) {
         AVS_CUDA(cudaFuncSetAttribute(scan_gemm_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        // the grid barrier between levels needs every CTA resident at once: ask the runtime how many clusters that is
+        int nc = s->num_sms / CG;
+        if (CG > 1) {
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3((unsigned)(s->num_sms / CG * CG));
+            qc.blockDim = dim3(GEMM_THREADS);
+            qc.dynamicSmemBytes = C::SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CG; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int got = 0;
+            if (cudaOccupancyMaxActiveClusters(&got, scan_gemm_kernel<CG>, &qc) == cudaSuccess && got > 0) nc = got < nc ? got : nc;
+            else cudaGetLastError();
+        } else {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_gemm_kernel<CG>, GEMM_THREADS, C::SMEM_BYTES) == cudaSuccess && per_sm >= 1) nc = s->num_sms;
+            else cudaGetLastError();
+        }
+        max_clusters[s->device & 63] = nc < 1 ? 1 : nc;
         attr[s->device & 63] = true;
     }
-    int64_t clusters = s->num_sms / CG;
-    if (clusters > lv.n_visit * n_qblocks) clusters = lv.n_visit * n_qblocks;
+    int64_t most = 1;                                     // the busiest level decides how many clusters are useful
+    for (int l = 0; l < plan.n_levels; ++l) { const int64_t t = plan.lv[l].n_visit * n_qblocks; most = t > most ? t : most; }
+    int64_t clusters = max_clusters[s->device & 63];
+    if (clusters > most) clusters = most;
     if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -469,17 +549,18 @@ int launch(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    AVS_CUDA(cudaLaunchKernelEx(&cfg, scan_gemm_kernel<CG>, mq, mx, s->count, n_qblocks, s->dpad / BLOCK_K, lv,
-                                (const u64*)s->sc.tau, s->sc.cand, s->sc.cnt, cap, (const uint32_t*)s->filter));
+    AVS_CUDA(cudaLaunchKernelEx(&cfg, scan_gemm_kernel<CG>, mq, mx, s->count, n_qblocks, s->dpad / BLOCK_K, plan,
+                                (const uint32_t*)s->filter));
     s->st_launches++;
     return AVS_OK;
 }
 
 }  // namespace
 
-int avs_launch_scan_gemm(avs_store* s, int nq, const AvsLevel& lv, int cap, cudaStream_t st) {
-    if (s->opt_cta_group == 1 || (nq <= BLOCK_M && s->opt_cta_group_small == 1)) return launch<1>(s, nq, lv, cap, st);
-    return launch<2>(s, nq, lv, cap, st);
+// One launch: every level in `plan` scanned by the tensor-core kernel with the level selects fused in.
+int avs_launch_scan_gemm(avs_store* s, int nq, const AvsScanPlan& plan, cudaStream_t st) {
+    if (s->opt_cta_group == 1 || (nq <= BLOCK_M && s->opt_cta_group_small == 1)) return launch<1>(s, nq, plan, st);
+    return launch<2>(s, nq, plan, st);
 }
 
 void avs_gemm_state_free(avs_store* s) { s->gemm_state = nullptr; }

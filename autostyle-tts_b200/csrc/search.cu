@@ -47,10 +47,12 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
                                                            double* __restrict__ qnorm, float* __restrict__ eps_gemv,
                                                            float* __restrict__ eps_gemm, u64* __restrict__ tau,
                                                            int* __restrict__ cnt, int* __restrict__ status,
-                                                           int* __restrict__ flagged, int* __restrict__ flagged2) {
+                                                           int* __restrict__ flagged, int* __restrict__ flagged2,
+                                                           unsigned int* __restrict__ gbar) {
     __shared__ double sh[4];
     const int qi = blockIdx.x;
     if (qi == 0 && threadIdx.x == 0) { flagged[0] = 0; flagged2[0] = 0; }   // repair queues of this search start empty
+    if (qi == 0 && threadIdx.x < 4) gbar[threadIdx.x] = 0u;                 // grid-barrier counters of the persistent kernels
     float* of = qf + (size_t)qi * dpad;
     __nv_bfloat16* ob = qb + (size_t)qi * dpad;
     if (qi >= nq) {  // padding slot: zero vector, never accepts
@@ -670,105 +672,294 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
         }
         if (threadIdx.x == 0) atomicAdd(dstat + 2, 1ull);
     } else if (threadIdx.x == 0) {                   // stage 2: exact scan of the whole shard
-        const int pos = atomicAdd(flagged2, 1);
-        if (pos < AVS_MAX_REPAIR_Q) {
-            flagged2[1 + pos] = q;
-            // lower bound of the true k-th score: from this stage if it rescored anything, else from finalize's
-            // K' candidates (out_s64 still holds their exact top-k)
-            rep_thr[pos] = (!lost && n >= need && need > 0) ? sm[need - 1].s
-                                                            : (need > 0 ? out_s64[(size_t)q * k + need - 1] : -INFINITY);
-            rep_cnt[pos] = 0;
-        } else {
-            status[q] |= ST_UNCERTIFIED;
-            atomicAdd(dstat + 1, 1ull);
-        }
+        const int pos = atomicAdd(flagged2, 1);        // every flagged query gets a slot: the repair kernel takes them in groups
+        flagged2[1 + pos] = q;
+        // lower bound of the true k-th score: from this stage if it rescored anything, else from finalize's
+        // K' candidates (out_s64 still holds their exact top-k); -inf when neither has k rows (the repair kernel then
+        // locates the k-th best score itself)
+        rep_thr[pos] = (!lost && n >= need && need > 0) ? sm[need - 1].s
+                                                        : (need > 0 ? out_s64[(size_t)q * k + need - 1] : -INFINITY);
+        rep_cnt[pos] = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact repair.  For every flagged query: float64 brute force over the fp32 master, collecting all
-// rows whose exact score reaches the k-th best exact score already known (a valid lower bound of
-// the true k-th best).  The collected set contains the true top-k; it is sorted exactly.
+// Exact repair: ONE cooperative kernel (grid barriers between its phases) that settles EVERY flagged query.
+//   * Flagged queries are taken in groups of up to 8: one pass over the fp32 master computes the float64 score of a
+//     row against the whole group (queries staged in shared memory, the row read once), so 36 flagged queries cost
+//     5 passes, not 36.
+//   * collect: rows whose exact score reaches the query's lower bound `thr` of the k-th best score go to the query's
+//     slice of a shared pool (slice = min(4096, pool / flagged) entries, so any number of flagged queries fits).
+//   * a query WITHOUT a usable bound (fewer than k candidates were collected: thr = -inf) or whose slice overflowed
+//     gets an exact one first: two histogram passes over its float-rounded scores (12 + 12 bits of the monotone
+//     key) locate the k-th best score to 2^-15 relative, which becomes `thr`; then it is collected (again).
+//   * finalize: a CTA per query sorts the collected rows by (score desc, id asc, row asc) and writes the top-k.
+// A query ends ST_UNCERTIFIED only if more rows than its slice holds tie with the k-th score inside that last bin.
+// The kernel exits at once when nothing is flagged (the common case).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) repair_scan_kernel(const float* __restrict__ master, const float* __restrict__ q,
-                                                          const double* __restrict__ qnorm, int64_t n_rows, int dim,
-                                                          int metric, const uint32_t* __restrict__ filt,
-                                                          const int* __restrict__ flagged,
-                                                          const double* __restrict__ rep_thr, double* __restrict__ rep_s,
-                                                          uint32_t* __restrict__ rep_row, int* __restrict__ rep_cnt) {
-    int nf = flagged[0];
-    if (nf == 0) return;
-    if (nf > AVS_MAX_REPAIR_Q) nf = AVS_MAX_REPAIR_Q;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int f = 0; f < nf; ++f) {
-        const int qi = flagged[1 + f];
-        const double thr = rep_thr[f], qn = qnorm[qi];
-        const float* qp = q + (size_t)qi * dim;
-        for (int64_t r = warp; r < n_rows; r += nwarps) {
-            if (filt && !((filt[r >> 5] >> (r & 31)) & 1u)) continue;
-            const double s = exact_score(master + (size_t)r * dim, qp, dim, qn, metric, lane);
-            if (lane == 0 && s >= thr) {
-                const int pos = atomicAdd(rep_cnt + f, 1);
-                if (pos < AVS_REPAIR_CAP) {
-                    rep_s[(size_t)f * AVS_REPAIR_CAP + pos] = s;
-                    rep_row[(size_t)f * AVS_REPAIR_CAP + pos] = (uint32_t)r;
-                }
-            }
-        }
-    }
+#define REPAIR_THREADS 512
+#define REPAIR_GMAX 8
+#define REPAIR_BINS 4096
+
+struct RepairArgs {
+    const float* master; const float* q; const double* qnorm; const int64_t* ids; const uint32_t* filt;
+    int64_t n_rows, n_eff; int dim, metric, k, group;
+    const int* flagged2; double* rep_thr; int* rep_cnt; int* rep_sel;     // rep_sel: [nq][2] histogram bin / rows above it
+    double* pool_s; uint32_t* pool_row; int64_t pool_items;
+    unsigned int* hist;                                                   // [REPAIR_GMAX][REPAIR_BINS]
+    int64_t* out_ids; float* out_scores; int64_t* out_rows; double* out_s64; int* status; u64* dstat;
+    unsigned int* gbar; unsigned int* err;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(1024) repair_finalize_kernel(const int* __restrict__ flagged, const double* __restrict__ rep_s,
-                                                               const uint32_t* __restrict__ rep_row, const int* __restrict__ rep_cnt,
-                                                               const int64_t* __restrict__ ids, int k, int64_t n_rows,
-                                                               int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
-                                                               int64_t* __restrict__ out_rows, double* __restrict__ out_s64,
-                                                               int* __restrict__ status, u64* __restrict__ dstat) {
-    extern __shared__ unsigned char raw[];
-    Hit* sm = reinterpret_cast<Hit*>(raw);
-    int nf = flagged[0];
-    if (nf > AVS_MAX_REPAIR_Q) nf = AVS_MAX_REPAIR_Q;
-    const int f = blockIdx.x;
-    if (f >= nf) return;
-    const int q = flagged[1 + f];
-    const int total = rep_cnt[f];
-    const int need = (int64_t)k < n_rows ? k : (int)n_rows;
-    if (total > AVS_REPAIR_CAP || total < need) {  // too many ties at the threshold: keep phase-1 output
-        if (threadIdx.x == 0) { status[q] |= ST_UNCERTIFIED; atomicAdd(dstat + 1, 1ull); }
-        return;
-    }
-    int P = 32;
-    while (P < total) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        Hit h;
-        if (i < total) { h.s = rep_s[(size_t)f * AVS_REPAIR_CAP + i]; h.row = rep_row[(size_t)f * AVS_REPAIR_CAP + i]; h.id = ids[h.row]; }
-        else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
-        sm[i] = h;
+// grid-wide barrier of a cooperatively launched kernel (the whole grid is resident); every thread calls it
+__device__ __forceinline__ void grid_barrier_all(unsigned int* gbar, unsigned int& epoch, unsigned int* err) {
+    __threadfence();
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        const unsigned int target = epoch * gridDim.x;
+        atomicAdd(gbar, 1u);
+        long long spins = 0;
+        while (ld_acquire_gpu_u32(gbar) < target) {
+            __nanosleep(64);
+            if (++spins > (1ll << 24)) { atomicAdd(err, 1u); break; }
+        }
+        __threadfence();
     }
     __syncthreads();
-    for (int k2 = 2; k2 <= P; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool desc = (i & k2) == 0;
-                    const Hit a = sm[i], b = sm[ixj];
-                    if (desc ? hit_better(b, a) : hit_better(a, b)) { sm[i] = b; sm[ixj] = a; }
+}
+
+// float64 scores of one master row against `ng` queries held in shared memory, same canonical accumulation order per
+// (row, query) as exact_score(): identical bits, so hits rescored by finalize_kernel and by the repair tie exactly.
+template <int GMAX>
+__device__ __forceinline__ void exact_scores_group(const float* __restrict__ x, const float* __restrict__ qs, int qstride, int ng,
+                                                   int dim, const double* __restrict__ qn, int metric, int lane, double (&out)[GMAX]) {
+    double dot[GMAX], xx = 0.0;
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) dot[g] = 0.0;
+    const int nquad = dim >> 2;                       // caller guarantees dim % 4 == 0 and 16-byte alignment
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    for (int base = 0; base < nquad; base += 64) {
+        float4 xv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = base + 32 * u + lane;
+            xv[u] = i < nquad ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = base + 32 * u + lane;
+            if (i < nquad) {
+                const double a0 = (double)xv[u].x, a1 = (double)xv[u].y, a2 = (double)xv[u].z, a3 = (double)xv[u].w;
+                xx = fma(a0, a0, xx); xx = fma(a1, a1, xx); xx = fma(a2, a2, xx); xx = fma(a3, a3, xx);
+#pragma unroll
+                for (int g = 0; g < GMAX; ++g) {
+                    if (g < ng) {
+                        const float4 qv = reinterpret_cast<const float4*>(qs + (size_t)g * qstride)[i];
+                        dot[g] = fma(a0, (double)qv.x, dot[g]);
+                        dot[g] = fma(a1, (double)qv.y, dot[g]);
+                        dot[g] = fma(a2, (double)qv.z, dot[g]);
+                        dot[g] = fma(a3, (double)qv.w, dot[g]);
+                    }
                 }
             }
-            __syncthreads();
         }
     }
-    for (int t = threadIdx.x; t < k; t += blockDim.x) {
-        const bool valid = t < total;
-        out_ids[(size_t)q * k + t] = valid ? sm[t].id : -1;
-        out_scores[(size_t)q * k + t] = valid ? (float)sm[t].s : -INFINITY;
-        if (out_rows) out_rows[(size_t)q * k + t] = valid ? (int64_t)sm[t].row : -1;
-        out_s64[(size_t)q * k + t] = valid ? sm[t].s : -INFINITY;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) dot[g] += __shfl_xor_sync(0xffffffffu, dot[g], o);
     }
-    if (threadIdx.x == 0) atomicAdd(dstat + 0, 1ull);
+    const double nx = sqrt(xx);
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) {
+        if (metric == AVS_METRIC_COSINE) {
+            const double den = nx * (g < ng ? qn[g] : 0.0);
+            out[g] = den > 0.0 ? dot[g] / den : 0.0;
+        } else out[g] = dot[g];
+    }
+}
+
+__global__ void __launch_bounds__(REPAIR_THREADS) repair_kernel(RepairArgs a) {
+    extern __shared__ unsigned char raw[];
+    int nf = a.flagged2[0];
+    if (nf == 0) return;                                                  // uniform: nobody reaches a barrier
+    __shared__ double s_thr[REPAIR_GMAX], s_qn[REPAIR_GMAX];
+    __shared__ int s_f[REPAIR_GMAX], s_q[REPAIR_GMAX], s_bin[REPAIR_GMAX];
+    const int need = (int64_t)a.k < a.n_eff ? a.k : (int)a.n_eff;
+    const int64_t nf_max = a.pool_items / AVS_MAX_KPRIME;
+    if (nf > nf_max) {                                                    // more flagged queries than the pool has minimal slices for
+        if (blockIdx.x == 0)
+            for (int f = (int)nf_max + threadIdx.x; f < nf; f += blockDim.x) { a.status[a.flagged2[1 + f]] |= ST_UNCERTIFIED; atomicAdd(a.dstat + 1, 1ull); }
+        nf = (int)nf_max;
+    }
+    int capq = (int)(a.pool_items / nf);
+    if (capq > AVS_REPAIR_CAP) capq = AVS_REPAIR_CAP;
+    unsigned int epoch = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * (REPAIR_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (REPAIR_THREADS / 32);
+    const bool vec = (a.dim & 3) == 0;                                    // master rows and the staged queries are 16-byte aligned then
+    float* qs = reinterpret_cast<float*>(raw);
+    const int qstride = (a.dim + 3) & ~3;
+
+    // mode 0: collect rows with score >= thr; mode 1 / 2: first / second histogram pass of the threshold search
+    auto scan = [&](int ng, unsigned mask, int mode) {
+        for (int64_t r = gwarp; r < a.n_rows; r += nwarps) {
+            if (a.filt && !((a.filt[r >> 5] >> (r & 31)) & 1u)) continue;
+            double sc[REPAIR_GMAX];
+            const float* x = a.master + (size_t)r * a.dim;
+            if (vec) exact_scores_group<REPAIR_GMAX>(x, qs, qstride, ng, a.dim, s_qn, a.metric, lane, sc);
+            else {
+#pragma unroll
+                for (int g = 0; g < REPAIR_GMAX; ++g)
+                    sc[g] = g < ng ? exact_score(x, a.q + (size_t)s_q[g] * a.dim, a.dim, s_qn[g], a.metric, lane) : 0.0;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < REPAIR_GMAX; ++g) {
+                    if (g >= ng || !((mask >> g) & 1u)) continue;
+                    if (mode == 0) {
+                        if (sc[g] >= s_thr[g]) {
+                            const int pos = atomicAdd(a.rep_cnt + s_f[g], 1);
+                            if (pos < capq) {
+                                a.pool_s[(size_t)s_f[g] * capq + pos] = sc[g];
+                                a.pool_row[(size_t)s_f[g] * capq + pos] = (uint32_t)r;
+                            }
+                        }
+                    } else {
+                        const uint32_t key = avs_f2ord((float)sc[g]);
+                        if (mode == 1) atomicAdd(a.hist + g * REPAIR_BINS + (key >> 20), 1u);
+                        else if ((int)(key >> 20) == s_bin[g]) atomicAdd(a.hist + g * REPAIR_BINS + ((key >> 8) & 0xFFFu), 1u);
+                    }
+                }
+            }
+        }
+    };
+    // histogram of the queries in `mask` -> (bin holding the `need`-th best, rows above that bin); block 0 writes rep_sel
+    auto hist_pass = [&](int ng, unsigned mask, int mode) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < REPAIR_GMAX * REPAIR_BINS; i += gridDim.x * blockDim.x) a.hist[i] = 0u;
+        grid_barrier_all(a.gbar, epoch, a.err);
+        scan(ng, mask, mode);
+        grid_barrier_all(a.gbar, epoch, a.err);
+        if (blockIdx.x == 0 && (threadIdx.x >> 5) < ng && ((mask >> (threadIdx.x >> 5)) & 1u)) {
+            const int g = threadIdx.x >> 5;
+            const int above0 = mode == 1 ? 0 : a.rep_sel[2 * s_f[g] + 1];
+            int acc = above0, found = -1, found_above = 0;
+            for (int b0 = REPAIR_BINS - 32; b0 >= 0 && found < 0; b0 -= 32) {           // bins from the top, 32 at a time
+                const int v = (int)a.hist[g * REPAIR_BINS + b0 + (31 - lane)];           // lane 0 = highest bin of the chunk
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+                const unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= need);
+                if (hit) {
+                    const int l0 = __ffs(hit) - 1;
+                    found = b0 + (31 - l0);
+                    found_above = acc + __shfl_sync(0xffffffffu, incl - v, l0);
+                }
+                acc += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) {
+                if (found < 0) { found = 0; found_above = acc; }                        // fewer than `need` rows in all: take everything
+                a.rep_sel[2 * s_f[g]] = found;
+                a.rep_sel[2 * s_f[g] + 1] = found_above;
+            }
+        }
+        grid_barrier_all(a.gbar, epoch, a.err);
+    };
+    // exact threshold for the queries in `mask`: k-th best float-rounded score located to 2^-15 relative
+    auto find_threshold = [&](int ng, unsigned mask) {
+        hist_pass(ng, mask, 1);
+        if (threadIdx.x < ng) s_bin[threadIdx.x] = a.rep_sel[2 * s_f[threadIdx.x]];
+        __syncthreads();
+        hist_pass(ng, mask, 2);
+        if (threadIdx.x < ng && ((mask >> threadIdx.x) & 1u)) {
+            const uint32_t key = ((uint32_t)s_bin[threadIdx.x] << 20) | ((uint32_t)a.rep_sel[2 * s_f[threadIdx.x]] << 8);
+            const double edge = (double)avs_ord2f(key);
+            // rows counted have float(score) >= edge, i.e. score >= edge - half an fp32 ulp: loosen by 2^-22 relative
+            const double thr = edge - fabs(edge) * 2.4e-7 - 1e-300;
+            s_thr[threadIdx.x] = (a.rep_sel[2 * s_f[threadIdx.x]] == 0 && s_bin[threadIdx.x] == 0) ? -INFINITY : thr;
+            if (blockIdx.x == 0) { a.rep_thr[s_f[threadIdx.x]] = s_thr[threadIdx.x]; a.rep_cnt[s_f[threadIdx.x]] = 0; }
+        }
+        grid_barrier_all(a.gbar, epoch, a.err);
+    };
+
+    for (int g0 = 0; g0 < nf; g0 += a.group) {
+        const int ng = nf - g0 < a.group ? nf - g0 : a.group;
+        __syncthreads();
+        if (threadIdx.x < ng) {
+            const int f = g0 + threadIdx.x, qi = a.flagged2[1 + f];
+            s_f[threadIdx.x] = f; s_q[threadIdx.x] = qi; s_qn[threadIdx.x] = a.qnorm[qi]; s_thr[threadIdx.x] = a.rep_thr[f];
+        }
+        if (vec)
+            for (int i = threadIdx.x; i < ng * qstride; i += blockDim.x) {
+                const int g = i / qstride, c = i - g * qstride;
+                qs[i] = c < a.dim ? a.q[(size_t)a.flagged2[1 + g0 + g] * a.dim + c] : 0.f;
+            }
+        __syncthreads();
+        unsigned need_thr = 0;                                            // no usable bound: find one first
+        for (int g = 0; g < ng; ++g) if (!(s_thr[g] > -INFINITY)) need_thr |= 1u << g;
+        if (need_thr) find_threshold(ng, need_thr);
+        scan(ng, (1u << ng) - 1, 0);
+        grid_barrier_all(a.gbar, epoch, a.err);
+        unsigned over = 0;                                                // slice overflowed: the bound was too loose
+        for (int g = 0; g < ng; ++g) if (a.rep_cnt[s_f[g]] > capq && !((need_thr >> g) & 1u)) over |= 1u << g;
+        if (over) {
+            grid_barrier_all(a.gbar, epoch, a.err);                       // everyone has read the counts before they are reset
+            find_threshold(ng, over);
+            scan(ng, over, 0);
+            grid_barrier_all(a.gbar, epoch, a.err);
+        }
+    }
+
+    // ---- finalize: one CTA per flagged query ----
+    Hit* sm = reinterpret_cast<Hit*>(raw);
+    for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+        __syncthreads();
+        const int q = a.flagged2[1 + f];
+        const int total = a.rep_cnt[f];
+        if (total > capq || total < need) {            // more ties at the k-th score than the slice holds: keep the earlier output
+            if (threadIdx.x == 0) { a.status[q] |= ST_UNCERTIFIED; atomicAdd(a.dstat + 1, 1ull); }
+            continue;
+        }
+        int P = 32;
+        while (P < total) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            Hit h;
+            if (i < total) { h.s = a.pool_s[(size_t)f * capq + i]; h.row = a.pool_row[(size_t)f * capq + i]; h.id = a.ids[h.row]; }
+            else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
+            sm[i] = h;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= P; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const bool desc = (i & k2) == 0;
+                        const Hit x = sm[i], y = sm[ixj];
+                        if (desc ? hit_better(y, x) : hit_better(x, y)) { sm[i] = y; sm[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int t = threadIdx.x; t < a.k; t += blockDim.x) {
+            const bool valid = t < total;
+            a.out_ids[(size_t)q * a.k + t] = valid ? sm[t].id : -1;
+            a.out_scores[(size_t)q * a.k + t] = valid ? (float)sm[t].s : -INFINITY;
+            if (a.out_rows) a.out_rows[(size_t)q * a.k + t] = valid ? (int64_t)sm[t].row : -1;
+            a.out_s64[(size_t)q * a.k + t] = valid ? sm[t].s : -INFINITY;
+        }
+        if (threadIdx.x == 0) atomicAdd(a.dstat + 0, 1ull);
+    }
 }
 
 __global__ void fill_empty_kernel(int64_t* ids, float* scores, int64_t* rows, double* s64, int64_t n) {
@@ -801,7 +992,8 @@ void avs_scratch_free(avs_store* s) {
     cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
     cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.dense_buf); cudaFree(c.rep_s); cudaFree(c.rep_row);
-    cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.gather_send); cudaFree(c.gather_recv);
+    cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.rep_sel); cudaFree(c.rep_hist); cudaFree(c.gbar);
+    cudaFree(c.gather_send); cudaFree(c.gather_recv);
     cudaFree(c.d_ids);
     if (c.h2d_q) cudaFree(c.h2d_q);
     if (c.h_out) cudaFreeHost(c.h_out);
@@ -830,19 +1022,29 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.topn, (size_t)nq2));
         AVS_CHECK(dev_alloc(&c.status, (size_t)nq2));
         AVS_CHECK(dev_alloc(&c.flagged, (size_t)nq2 + 1));
+        AVS_CHECK(dev_alloc(&c.flagged2, (size_t)nq2 + 1));
+        AVS_CHECK(dev_alloc(&c.rep_cnt, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.rep_thr, (size_t)nq2));
+        AVS_CHECK(dev_alloc(&c.rep_sel, (size_t)nq2 * 2));
+        // exact-repair pool, shared by the flagged queries of a search (slice = min(4096, pool / flagged) rows each):
+        // room for 256 rows of every query of the largest batch, at least 1 M and at most 16 M rows
+        size_t pool = (size_t)nq2 * AVS_MAX_KPRIME;
+        if (pool < ((size_t)1 << 20)) pool = (size_t)1 << 20;
+        if (pool > ((size_t)1 << 24)) pool = (size_t)1 << 24;
+        AVS_CHECK(dev_alloc(&c.rep_s, pool));
+        AVS_CHECK(dev_alloc(&c.rep_row, pool));
+        c.pool_items = pool;
     }
     if (grow_q || grow_cap) AVS_CHECK(dev_alloc(&c.cand, (size_t)nq2 * cap2));
     if (grow_q || grow_kp) {
         AVS_CHECK(dev_alloc(&c.topkeys, (size_t)nq2 * kp2));
     }
     if (grow_q || grow_k) AVS_CHECK(dev_alloc(&c.out_s64, (size_t)nq2 * k2));
-    if (!c.flagged2) {
-        AVS_CHECK(dev_alloc(&c.flagged2, (size_t)1 + AVS_MAX_REPAIR_Q));
+    if (!c.dense_buf) {
         AVS_CHECK(dev_alloc(&c.dense_buf, (size_t)(AVS_DENSE_MAX_NQ + 8) * AVS_DENSE_CAP));
-        AVS_CHECK(dev_alloc(&c.rep_s, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
-        AVS_CHECK(dev_alloc(&c.rep_row, (size_t)AVS_MAX_REPAIR_Q * AVS_REPAIR_CAP));
-        AVS_CHECK(dev_alloc(&c.rep_cnt, (size_t)AVS_MAX_REPAIR_Q));
-        AVS_CHECK(dev_alloc(&c.rep_thr, (size_t)AVS_MAX_REPAIR_Q));
+        AVS_CHECK(dev_alloc(&c.rep_hist, (size_t)8 * 4096));
+        AVS_CHECK(dev_alloc(&c.gbar, (size_t)4));
+        AVS_CUDA(cudaMemset(c.gbar, 0, 4 * sizeof(unsigned int)));
     }
     c.nq_cap = nq2; c.kprime_cap = kp2; c.cap_cap = cap2; c.k_cap = k2;
     return AVS_OK;
@@ -932,7 +1134,10 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     const size_t scan_bytes = (size_t)s->count * s->dpad * 2;
     const bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 &&
                         ((nq <= 2 && s->dpad <= 1024) || (nq >= 3 && nq <= 8 && scan_bytes <= ((size_t)8 << 30)));
-    const bool use_gemm = !hybrid && ((s->opt_scan_path == 2) || (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch));
+    // auto mode without the hybrid pipeline: tensor-core scan from `gemm_min_batch` queries on, except 1-2 queries of
+    // D > 1024, where the warp-dot kernel streams 5 % faster
+    const bool use_gemm = !hybrid && ((s->opt_scan_path == 2) ||
+                                      (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch && !(nq <= 2 && s->dpad > 1024)));
     // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
     // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
@@ -991,7 +1196,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         }
     }
 
-    s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;
+    s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;   // warp-dot path: its final level
     s->st_last_kprime = kprime;
     s->st_last_levels = L;
     const bool hybrid_on = hybrid && L > 1 && lv[0].dense;   // single-level searches stay on the gemv kernels
@@ -1004,38 +1209,81 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // spacing), the last threshold is kept 2.5 eps under the k-th score so that wide rescoring suffices.
     if (s->h_stats && s->h_stats[0] > s->seen_repaired) { s->seen_repaired = s->h_stats[0]; s->eps_rule = true; }
     const int n_slots = any_gemm ? nq_pad : (nq + 7) / 8 * 8;   // padding slots the scan will touch
+    // Kernels that synchronise their whole grid (persistent scan, repair) must not share the device with another
+    // such kernel from a different stream (each could hold SMs the other waits for): chain them through one event.
+    static cudaEvent_t persist_ev[64] = {};
+    cudaEvent_t& pev = persist_ev[s->device & 63];
+    if (!pev) AVS_CUDA(cudaEventCreateWithFlags(&pev, cudaEventDisableTiming));
+    else AVS_CUDA(cudaStreamWaitEvent(st, pev, 0));
     prep_queries_kernel<<<n_slots, 128, 0, st>>>(q, nq, s->dim, s->dpad, s->metric, s->gstat, c.qf, c.qb, c.qnorm,
-                                                c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status, c.flagged, c.flagged2);
+                                                c.eps_gemv, c.eps_gemm, c.tau, c.cnt, c.status, c.flagged, c.flagged2, c.gbar);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
 
+    // exact-repair kernel: queries per pass over the master (staged in shared memory) and its co-resident grid
+    const int qstride = (s->dim + 3) & ~3;
+    int rep_group = (96 * 1024) / (qstride * 4);
+    rep_group = rep_group > REPAIR_GMAX ? REPAIR_GMAX : (rep_group < 1 ? 1 : rep_group);
+    size_t rep_smem = (size_t)rep_group * qstride * 4;
+    if (rep_smem < AVS_REPAIR_CAP * sizeof(Hit)) rep_smem = AVS_REPAIR_CAP * sizeof(Hit);
     static bool attr_done[64] = {};   // function attributes are per device
+    static int rep_ctas_per_sm[64] = {};
     if (!attr_done[s->device & 63]) {
         AVS_CUDA(cudaFuncSetAttribute(select_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        AVS_CUDA(cudaFuncSetAttribute(repair_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(AVS_REPAIR_CAP * sizeof(Hit))));
+        AVS_CUDA(cudaFuncSetAttribute(repair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         AVS_CUDA(cudaFuncSetAttribute(wide_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(AVS_WIDE_MAX * sizeof(Hit))));
         attr_done[s->device & 63] = true;
     }
+    if (rep_ctas_per_sm[s->device & 63] == 0 || s->rep_smem_seen != rep_smem) {
+        int per_sm = 0;
+        AVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, repair_kernel, REPAIR_THREADS, rep_smem));
+        if (per_sm < 1) { avs_set_error("repair kernel does not fit an SM with %zu bytes of shared memory", rep_smem); return AVS_E_CUDA; }
+        rep_ctas_per_sm[s->device & 63] = per_sm;
+        s->rep_smem_seen = rep_smem;
+    }
 
-    for (int l = 0; l < L; ++l) {
+    // Level schedule -> launches.  Tensor-core path: ONE persistent launch scans every level and runs the selects
+    // between them (scan_gemm.cu).  Hybrid small-batch path: warp-dot dense level + its select, then one persistent
+    // launch for the remaining levels.  Warp-dot path: a scan and a select launch per level.
+    const int first_gemm_level = use_gemm ? 0 : (hybrid_on ? 1 : L);
+    for (int l = 0; l < first_gemm_level; ++l) {
         const bool final_level = (l == L - 1);
         size_t slot = 0;
         const bool timed = final_level && timing_begin(s, st, &slot);
-        if (use_gemm || (hybrid_on && l > 0)) {
-            AVS_CHECK(avs_launch_scan_gemm(s, nq, lv[l], cap, st));
-        } else {
-            for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
-        }
+        for (int q0 = 0; q0 < nq; q0 += 8) AVS_CHECK(avs_launch_scan_gemv(s, q0, nq - q0 < 8 ? nq - q0 : 8, lv[l], cap, st));
         if (timed) timing_end(s, st, slot);
         SelectArgs sa = {c.cand, c.cnt, cap, c.tau, j_ranks[l], final_level ? 1 : 0, kprime, n_eff, c.topkeys, c.topn,
                          bound, c.status, lv[l].dense ? (int)(lv[l].n_visit * AVS_GROUP_ROWS) : 0, nq,
-                         (lv[l].dense && !use_gemm) ? c.dense_buf : nullptr, AVS_DENSE_CAP,
-                         eps_used, (l == L - 2 && fine_levels && s->eps_rule) ? k : 0};
+                         lv[l].dense ? c.dense_buf : nullptr, AVS_DENSE_CAP,
+                         eps_used, 0};
         select_level_kernel<<<nq, nq <= 64 ? 1024 : 256, (size_t)cap * 8, st>>>(sa);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
+    }
+    if (first_gemm_level < L) {
+        AvsScanPlan plan;
+        memset(&plan, 0, sizeof(plan));
+        plan.n_levels = L - first_gemm_level;
+        plan.last_is_final = 1;
+        plan.nq = nq; plan.kprime = kprime; plan.cap = cap; plan.n_eff = n_eff;
+        int64_t rows_scanned = 0;
+        for (int l = first_gemm_level; l < L; ++l) {
+            const int i = l - first_gemm_level;
+            plan.lv[i] = lv[l];
+            plan.j_rank[i] = j_ranks[l];
+            plan.k_eps[i] = (l == L - 2 && fine_levels && s->eps_rule) ? k : 0;
+            rows_scanned += lv[l].n_visit * AVS_GROUP_ROWS;
+        }
+        plan.tau = c.tau; plan.cand = c.cand; plan.cnt = c.cnt; plan.topkeys = c.topkeys; plan.topn = c.topn;
+        plan.bound = bound; plan.status = c.status; plan.eps = eps_used;
+        plan.gbar = c.gbar + 0;
+        plan.err = reinterpret_cast<unsigned int*>(s->dstat + 3);
+        s->st_last_final_rows = rows_scanned < s->count ? rows_scanned : s->count;   // rows the timed launch scans
+        size_t slot = 0;
+        const bool timed = timing_begin(s, st, &slot);
+        AVS_CHECK(avs_launch_scan_gemm(s, nq, plan, st));
+        if (timed) timing_end(s, st, slot);
     }
 
     finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
@@ -1049,17 +1297,21 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         c.rep_cnt, s->dstat);
     s->st_launches++;
     AVS_CUDA(cudaGetLastError());
-    repair_scan_kernel<<<s->num_sms * 4, 256, 0, st>>>(s->master, q, c.qnorm, s->count, s->dim, s->metric, s->filter, c.flagged2,
-                                                       c.rep_thr, c.rep_s, c.rep_row, c.rep_cnt);
-    s->st_launches++;
-    AVS_CUDA(cudaGetLastError());
-    const int rep_blocks = nq < AVS_MAX_REPAIR_Q ? nq : AVS_MAX_REPAIR_Q;
-    repair_finalize_kernel<<<rep_blocks, 1024, AVS_REPAIR_CAP * sizeof(Hit), st>>>(
-        c.flagged2, c.rep_s, c.rep_row, c.rep_cnt, s->ids, k, n_eff, out_ids, out_scores, out_rows, c.out_s64, c.status,
-        s->dstat);
-    s->st_launches++;
-    AVS_CUDA(cudaGetLastError());
-    if (s->h_stats) AVS_CUDA(cudaMemcpyAsync(s->h_stats, s->dstat, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    {
+        RepairArgs ra;
+        ra.master = s->master; ra.q = q; ra.qnorm = c.qnorm; ra.ids = s->ids; ra.filt = s->filter;
+        ra.n_rows = s->count; ra.n_eff = n_eff; ra.dim = s->dim; ra.metric = s->metric; ra.k = k; ra.group = rep_group;
+        ra.flagged2 = c.flagged2; ra.rep_thr = c.rep_thr; ra.rep_cnt = c.rep_cnt; ra.rep_sel = c.rep_sel;
+        ra.pool_s = c.rep_s; ra.pool_row = c.rep_row; ra.pool_items = (int64_t)c.pool_items; ra.hist = c.rep_hist;
+        ra.out_ids = out_ids; ra.out_scores = out_scores; ra.out_rows = out_rows; ra.out_s64 = c.out_s64; ra.status = c.status;
+        ra.dstat = s->dstat; ra.gbar = c.gbar + 1; ra.err = reinterpret_cast<unsigned int*>(s->dstat + 3);
+        void* args[] = {&ra};
+        AVS_CUDA(cudaLaunchCooperativeKernel((const void*)repair_kernel, dim3((unsigned)(rep_ctas_per_sm[s->device & 63] * s->num_sms)),
+                                             dim3(REPAIR_THREADS), args, rep_smem, st));
+        s->st_launches++;
+    }
+    AVS_CUDA(cudaEventRecord(pev, st));
+    if (s->h_stats) AVS_CUDA(cudaMemcpyAsync(s->h_stats, s->dstat, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     return AVS_OK;
 }
 
@@ -1160,11 +1412,11 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "exchange_us") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_exchange_us(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k == "last_uncertified") *out = s->st_last_uncertified;   // of the last avs_search_host call; no device sync
-    else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries") {
+    else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries" || k == "barrier_timeouts") {
         AVS_CUDA(cudaSetDevice(s->device));
-        u64 h[3];
+        u64 h[4];
         AVS_CUDA(cudaMemcpy(h, s->dstat, sizeof(h), cudaMemcpyDeviceToHost));
-        *out = (int64_t)(k == "repaired_queries" ? h[0] : k == "uncertified_queries" ? h[1] : h[2]);
+        *out = (int64_t)(k == "repaired_queries" ? h[0] : k == "uncertified_queries" ? h[1] : k == "wide_rescored_queries" ? h[2] : (h[3] & 0xFFFFFFFFull));
     } else { avs_set_error("avs_get_stat: unknown stat '%s'", key); return AVS_E_INVALID; }
     return AVS_OK;
 }

@@ -1,0 +1,259 @@
+// Warp-per-query level select (K4), used inside the persistent tensor-core scan kernel: after a level has been
+// scanned by the whole grid, every warp of the grid takes queries in turn and
+//   intermediate level: finds the rank-j key of what the query has collected (the next level's threshold) and
+//                       compacts the survivors to the front of the query's candidate buffer;
+//   final level:        hands the best K' keys to the rescoring stage together with `bound`, an upper bound on the
+//                       scan score of every row that is NOT among them.
+// Same semantics as select_level_kernel (search.cu), which stays for the warp-dot (gemv) path.
+//   <= 256 keys  : bitonic sort in registers (8 keys per lane)
+//   dense level  : pivot method - the rank-j value of the 32 lane maxima is a lower bound of the rank-j key; the few
+//                  keys above it are compacted into the warp's shared-memory list and sorted in registers
+//   otherwise    : 8-pass byte-wise radix select (warp histogram in shared memory) + ordered in-place compaction
+#pragma once
+
+#include "avs_internal.h"
+
+#define AVS_ST_OVERFLOW 1
+
+// The select reads its arguments straight from the kernel's AvsScanPlan (a __grid_constant__ parameter: no copy on
+// the stack); n_eff = rows that may be returned (filter-allowed count).
+typedef AvsScanPlan WarpSelectArgs;
+
+template <int EPL>
+__device__ __forceinline__ void wsel_sort_desc(u64 (&k)[EPL], int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * EPL; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const int pr = r ^ jr;
+                    if (pr > r) {
+                        const bool desc = (((32 * r) & k2) == 0);
+                        const u64 x = k[r], y = k[pr];
+                        const bool sw = desc ? (x < y) : (x > y);
+                        k[r] = sw ? y : x;
+                        k[pr] = sw ? x : y;
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const bool desc = (((lane + 32 * r) & k2) == 0);
+                    const u64 other = __shfl_xor_sync(0xffffffffu, k[r], j);
+                    const u64 mx = k[r] > other ? k[r] : other, mn = k[r] > other ? other : k[r];
+                    k[r] = (desc == lower) ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
+// element e (0-based rank) of a register-sorted array: lane e % 32, register e / 32
+template <int EPL>
+__device__ __forceinline__ u64 wsel_pick(const u64 (&k)[EPL], int e) {
+    u64 v = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) v = (r == (e >> 5)) ? k[r] : v;
+    return __shfl_sync(0xffffffffu, v, e & 31);
+}
+
+// the final level's `bound` (see select_emit_scalar in search.cu); one lane calls it
+__device__ __forceinline__ void wsel_emit_final(const WarpSelectArgs& a, int q, int n, u64 key_kp, bool lost) {
+    const int m = n < a.kprime ? n : a.kprime;
+    a.topn[q] = m;
+    float b;
+    int st = 0;
+    if (lost || (a.status[q] & AVS_ST_OVERFLOW)) { b = INFINITY; st = AVS_ST_OVERFLOW; }   // entries were lost
+    else if (n > a.kprime) b = avs_key_score(key_kp);                  // rows outside the K' candidates <= K'-th key
+    else if ((int64_t)n >= a.n_eff) b = -INFINITY;                    // every row is a candidate
+    else b = a.tau[q] == 0ull ? -INFINITY : avs_key_score(a.tau[q]);   // rows outside < threshold
+    a.bound[q] = b;
+    a.status[q] |= st;
+}
+
+// `list`: 256 u64 of shared memory owned by this warp (also used as a 256-bin int histogram by the radix path).
+__device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, int lane, int j_rank, bool is_final,
+                                               int dense_total, int k_eps, u64* list) {
+    u64* c = a.cand + (size_t)q * a.cap;
+    const int total_in = dense_total > 0 ? dense_total : a.cnt[q];
+    const bool lost = dense_total == 0 && total_in > a.cap;       // more keys were offered than the buffer holds
+    const int n = total_in < a.cap ? total_in : a.cap;            // slots to look at
+    int jj = j_rank;
+    if (lost) { jj = (int)(((long long)j_rank * a.cap) / total_in); if (jj < 1) jj = 1; }
+
+    // ---- dense (threshold-free) level with a small rank: pivot method, two passes over the keys ----
+    // the rank-j value of the 32 lane maxima is a lower bound of the rank-j key; the keys above it (j .. a few dozen) are
+    // compacted into the warp's list and then take the register-sort path below
+    const u64* src = c;
+    int n_src = n;
+    if (n > 256 && dense_total > 0 && !is_final && jj <= 32) {
+        u64 lm = 0;
+        for (int i = lane; i < n; i += 32) { const u64 key = c[i]; lm = key > lm ? key : lm; }
+        u64 k1[1] = {lm};
+        wsel_sort_desc<1>(k1, lane);
+        const u64 P = __shfl_sync(0xffffffffu, k1[0], jj - 1);   // j distinct keys are >= P
+        if (P != 0ull) {
+            int m = 0;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const u64 key = i < n ? c[i] : 0ull;
+                const bool in = key >= P;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                const int pos = m + __popc(bal & ((1u << lane) - 1));
+                if (in && pos < 256) list[pos] = key;
+                m += __popc(bal);
+            }
+            __syncwarp();
+            if (m <= 256) { src = list; n_src = m; }              // m >= jj by construction
+        }
+        // else: few real keys (row filter) or a pile-up at the pivot -> radix select below
+    }
+
+    if (n_src <= 256) {
+        // ---- everything fits 8 registers per lane: sort ----
+        u64 k8[8];
+        int nz = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = lane + 32 * r;
+            k8[r] = i < n_src ? src[i] : 0ull;
+            nz += k8[r] != 0ull;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        wsel_sort_desc<8>(k8, lane);
+        const int n_real = nz;                                    // the dense level's padding slots hold key 0 and sort last
+        if (!is_final) {
+            int keep = n_real >= jj ? jj : n_real;
+            u64 tau_new = n_real >= jj ? wsel_pick<8>(k8, jj - 1) : a.tau[q];
+            // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
+            if (k_eps > 0 && n_real >= k_eps && !lost) {
+                const u64 kk = wsel_pick<8>(k8, k_eps - 1);
+                const u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+                if (t_eps < tau_new) {
+                    tau_new = t_eps;
+                    int above = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) above += (k8[r] >= tau_new && k8[r] != 0ull) ? 1 : 0;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+                    keep = above;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { const int i = lane + 32 * r; if (i < keep) c[i] = k8[r]; }
+            if (lane == 0) {
+                a.tau[q] = tau_new;
+                a.cnt[q] = keep;
+                if (lost) a.status[q] |= AVS_ST_OVERFLOW;
+            }
+        } else {
+            const int m = n_real < a.kprime ? n_real : a.kprime;
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = lane + 32 * r;
+                if (i < a.kprime) a.topkeys[(size_t)q * a.kprime + i] = i < m ? k8[r] : 0ull;
+                if (i < n) c[i] = k8[r];                          // sorted: the wide-rescoring stage reads it
+            }
+            const u64 key_kp = wsel_pick<8>(k8, a.kprime - 1 < 255 ? a.kprime - 1 : 255);
+            if (lane == 0) {
+                a.cnt[q] = dense_total > 0 ? n : total_in;
+                wsel_emit_final(a, q, n_real, key_kp, lost);
+            }
+        }
+        return;
+    }
+
+    // ---- general case: radix select of the rank-`want` key, then a compaction ----
+    int* hist = reinterpret_cast<int*>(list);
+    int nzc = 0;
+    for (int i = lane; i < n; i += 32) nzc += c[i] != 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
+    const int n_real = nzc;
+    const int want = is_final ? (n_real < a.kprime ? n_real : a.kprime) : (n_real >= jj ? jj : n_real);
+    u64 prefix = 0, maskb = 0;
+    int rank = want - 1;
+    if (want > 0) {
+        for (int byte = 7; byte >= 0; --byte) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+            __syncwarp();
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const u64 key = i < n ? c[i] : 0ull;
+                const bool in = i < n && key != 0ull && (key & maskb) == prefix;
+                const int bin = in ? (int)((key >> (8 * byte)) & 0xFFull) : 256 + lane;   // non-members: unique dummies
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (in && lane == __ffs(peers) - 1) hist[bin] += __popc(peers);          // one lane per distinct bin: no conflict
+                __syncwarp();
+            }
+            // lane l owns bins 255-8l .. 248-8l (descending key order)
+            int loc[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { loc[b] = hist[255 - 8 * lane - b]; sum += loc[b]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            int accb = incl - sum;
+            int sel_bin = -1, sel_acc = 0;
+            if (rank >= accb && rank < incl) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (sel_bin < 0 && rank < accb + loc[b]) { sel_bin = 255 - 8 * lane - b; sel_acc = accb; }
+                    accb += loc[b];
+                }
+            }
+            const unsigned owner = __ballot_sync(0xffffffffu, sel_bin >= 0);
+            const int src = __ffs(owner) - 1;
+            sel_bin = __shfl_sync(0xffffffffu, sel_bin, src);
+            sel_acc = __shfl_sync(0xffffffffu, sel_acc, src);
+            prefix |= (u64)sel_bin << (8 * byte);
+            maskb |= 0xFFull << (8 * byte);
+            rank -= sel_acc;
+            __syncwarp();
+        }
+    }
+    const u64 Pk = want > 0 ? prefix : ~0ull;                      // the rank-(want-1) key; exactly `want` keys are >= it
+    if (!is_final) {
+        // ordered in-place compaction: the write cursor never passes the read cursor
+        int m = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const u64 key = i < n ? c[i] : 0ull;
+            const bool in = key >= Pk && key != 0ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            __syncwarp();
+            if (in) c[m + __popc(bal & ((1u << lane) - 1))] = key;
+            m += __popc(bal);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (n_real >= jj) a.tau[q] = Pk;
+            a.cnt[q] = want;
+            if (lost) a.status[q] |= AVS_ST_OVERFLOW;
+        }
+    } else {
+        int m = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const u64 key = i < n ? c[i] : 0ull;
+            const bool in = key >= Pk && key != 0ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) a.topkeys[(size_t)q * a.kprime + m + __popc(bal & ((1u << lane) - 1))] = key;
+            m += __popc(bal);
+        }
+        for (int i = want + lane; i < a.kprime; i += 32) a.topkeys[(size_t)q * a.kprime + i] = 0ull;
+        if (lane == 0) {
+            a.cnt[q] = dense_total > 0 ? n : total_in;             // dense level: slots (zero = empty), not keys
+            wsel_emit_final(a, q, n_real, Pk, lost);
+        }
+    }
+    __syncwarp();
+}

@@ -235,9 +235,16 @@ def test_hot_kernels_stay_lean_and_blackwell_native(pkg):
     gemv = [f for n, f in funcs.items() if "scan_gemv_kernel" in n]
     assert len(gemm) == 2 and len(gemv) == 4
     for f in gemm:
+        # the persistent kernel carries the warp-per-query level select (a 256-key register sort and a radix select: ~14 k instructions that
+        # run between levels, outside the hot tile loop) next to the ~5 k instructions of the scan itself
         n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,}\*/", f, flags=re.M))
-        assert n_instr < 7000, f"tensor-core scan grew to {n_instr} SASS instructions"
-        assert not re.search(r"\b(LDL|STL)\b", f), "tensor-core scan spills registers"
+        assert n_instr < 24000, f"tensor-core scan grew to {n_instr} SASS instructions"
+        # no local-memory traffic inside the hot tile loop (everything between the first and the last tcgen05.ld); the
+        # out-of-line level select saves registers on the stack at its entry, which is outside that span
+        lines = f.splitlines()
+        ldtm = [i for i, ln in enumerate(lines) if "LDTM" in ln]
+        hot = "\n".join(lines[ldtm[0]:ldtm[-1] + 1])
+        assert not re.search(r"\b(LDL|STL)\b", hot), "tensor-core scan spills registers in its tile loop"
         assert "UTCHMMA" in f and "UTMALDG" in f and "LDTM" in f and "UTCBAR" in f       # tcgen05.mma / TMA / tcgen05.ld / commit
     assert any("UTCHMMA.2CTA" in f for f in gemm)
     for f in gemv:
