@@ -211,17 +211,31 @@ class MilvusClient:
         if len(data) == 0:
             return {"insert_count": 0, "ids": []}
         declared = {f["name"] for f in coll.fields}
-        vecs = np.empty((len(data), coll.dim), dtype=np.float32)
+        # vectors: one bulk conversion when every row carries a well-formed vector (the common case; a 10^6-row insert
+        # must not convert row by row), the per-row path only to produce the reference's error messages
+        vecs = None
+        try:
+            bulk = np.asarray([row[coll.vec_name] for row in data], dtype=np.float32)
+            if bulk.ndim == 2 and bulk.shape == (len(data), coll.dim):
+                vecs = np.ascontiguousarray(bulk)
+        except (KeyError, TypeError, ValueError):
+            vecs = None
+        bulk_ok = vecs is not None
+        if not bulk_ok:
+            vecs = np.empty((len(data), coll.dim), dtype=np.float32)
         pks, metas, rows_for_disk, dyn_for_disk = [], [], [], []
         for i, row in enumerate(data):
             if not isinstance(row, dict):
                 raise MilvusException(f"wrong type of argument 'data[{i}]', expected 'Dict', got '{type(row).__name__}'")
             if coll.vec_name not in row:
                 raise MilvusException(f"Insert missed an field `{coll.vec_name}` to collection without set nullable==true or set default_value")
-            v = np.asarray(row[coll.vec_name], dtype=np.float32).reshape(-1)
-            if v.shape[0] != coll.dim:
-                raise MilvusException(f"the length({v.shape[0]}) of float data should divide the dim({coll.dim})")
-            vecs[i] = v
+            if bulk_ok:
+                v = vecs[i]
+            else:
+                v = np.asarray(row[coll.vec_name], dtype=np.float32).reshape(-1)
+                if v.shape[0] != coll.dim:
+                    raise MilvusException(f"the length({v.shape[0]}) of float data should divide the dim({coll.dim})")
+                vecs[i] = v
             if coll.auto_id:
                 if coll.pk_name in row:
                     raise MilvusException(f"Attempt to insert an unexpected field `{coll.pk_name}` to collection without enabling dynamic field"
@@ -270,6 +284,45 @@ class MilvusClient:
         if self._file is not None:
             self._file.append(coll.name, coll.fields, coll.pk_name, rows_for_disk, dyn_for_disk)
         return {"insert_count": len(data), "ids": list(pks), "cost": 0}
+
+    # ------------------------------------------------------------------ bulk snapshot
+    def save_snapshot(self, collection_name: str, path: str):
+        """Raw snapshot of a collection for 10^7-10^8-row stores: `path` = ids + fp32 vectors straight from the device
+        (avs_save), `path + ".meta.json"` = schema, primary keys and scalar / dynamic fields.  The per-row Milvus Lite
+        file (`MilvusClient("x.db")`, what the reference re-opens: /root/reference/milvus/search.py:197-210) stays the
+        persistence of small collections."""
+        import json
+        coll = self._coll(collection_name)
+        try:
+            self._ensure_store(coll).save(path)
+        except AvsError as e:
+            raise MilvusException(e.message, e.code) from e
+        with open(path + ".meta.json", "w", encoding="utf-8") as f:
+            json.dump({"name": coll.name, "dim": coll.dim, "metric": coll.metric, "pk_name": coll.pk_name, "vec_name": coll.vec_name,
+                       "auto_id": coll.auto_id, "fields": coll.fields, "enable_dynamic": coll.enable_dynamic,
+                       "index_params": coll.index_params, "next_auto": coll.next_auto, "pks": coll.pks, "meta": coll.meta}, f)
+
+    def load_snapshot(self, path: str, collection_name: Optional[str] = None) -> str:
+        """Restores a collection saved by save_snapshot into this client (device store rebuilt by avs_load: the bf16 scan
+        copy and norms come from the normalise-on-insert kernel, not from disk).  Returns the collection name."""
+        import json
+        with open(path + ".meta.json", encoding="utf-8") as f:
+            m = json.load(f)
+        name = collection_name or m["name"]
+        if name in self._colls:
+            raise MilvusException(f"collection {name} already exists")
+        coll = _Collection(name, m["dim"], m["metric"], m["pk_name"], m["vec_name"], m["auto_id"], m["fields"], m["enable_dynamic"],
+                           index_params=m.get("index_params"))
+        coll.pks, coll.meta, coll.next_auto = m["pks"], m["meta"], m.get("next_auto", 1)
+        try:
+            coll.store = Store.load(path, device=self.device)
+        except AvsError as e:
+            raise MilvusException(e.message, e.code) from e
+        if len(coll.store) != len(coll.pks):
+            coll.store.close()
+            raise MilvusException(f"snapshot {path}: {len(coll.store)} vectors but {len(coll.pks)} metadata rows")
+        self._colls[name] = coll
+        return name
 
     # ------------------------------------------------------------------ search
     def search(self, collection_name: str, data: Any = None, filter: Optional[str] = "", limit: int = 10,

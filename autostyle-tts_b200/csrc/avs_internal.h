@@ -98,6 +98,7 @@ struct AvsScanPlan {
     u64* tau; u64* cand; int* cnt; u64* topkeys; int* topn; float* bound; int* status; const float* eps;
     unsigned int* gbar;                 // grid barrier counter (zeroed by prep_queries_kernel)
     unsigned int* err;                  // bumped when a bounded barrier spin gives up
+    u64* trace;                         // optional [4 * AVS_MAX_LEVELS + 2] globaltimer stamps of CTA 0 (profiling option "trace")
 };
 
 struct AvsScratch {
@@ -119,6 +120,7 @@ struct AvsScratch {
     // repair
     int* flagged = nullptr;       // [1 + nq] stage 1 (wide rescoring): count, then query indices
     int* flagged2 = nullptr;      // [1 + nq] stage 2 (exact scan): count, then query indices
+    u64* trace = nullptr;         // [64] phase timestamps of the last persistent scan (option "trace")
     unsigned int* gbar = nullptr; // [4] grid-barrier counters of the persistent kernels (scan, repair), zeroed by prep
     double* rep_s = nullptr;      // [pool_items] exact-repair pool: scores ...
     uint32_t* rep_row = nullptr;  // [pool_items] ... and rows, cut into one slice per flagged query
@@ -186,6 +188,7 @@ struct avs_store {
     int opt_cta_group_small = 1;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
     int opt_dense_rows = AVS_DENSE_CAP;   // rows of the gemv path's threshold-free level (<= AVS_DENSE_CAP)
     int opt_hybrid = 1;              // auto mode, <= 8 queries: gemv dense level, tensor-core scan for the later levels
+    int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;
 };

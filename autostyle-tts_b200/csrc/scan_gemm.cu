@@ -308,6 +308,11 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             pend_n = 0;
         };
         unsigned int epoch = 0;
+        const bool tracer = plan.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+        auto stamp = [&](int slot) {
+            if (tracer) { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); plan.trace[slot] = t; }
+        };
+        stamp(0);
         for (int l = 0; l < plan.n_levels; ++l) {
         const AvsLevel& lv = plan.lv[l];
         const int64_t n_tiles = lv.n_visit * n_qblocks;
@@ -445,8 +450,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         flush_pending();
+        stamp(1 + 4 * l);                              // this CTA's tiles of the level are done
         // ---- level done on this CTA: wait for the whole grid, then select (warp per query), then the next level ----
         grid_barrier_epi(plan.gbar, epoch, plan.err);
+        stamp(2 + 4 * l);                              // the whole grid has finished the level
         {
             const bool final_level = plan.last_is_final && l == plan.n_levels - 1;
             u64* const list = stash_smem + (size_t)(warp - 4) * 256;           // 2 KB of the (now idle) survivor stash per warp
@@ -454,7 +461,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
                 warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);
         }
+        stamp(3 + 4 * l);                              // this CTA's share of the selects is done
         if (l + 1 < plan.n_levels) grid_barrier_epi(plan.gbar, epoch, plan.err);
+        stamp(4 + 4 * l);                              // every query has its new threshold
         }
     }
 

@@ -7,6 +7,7 @@
 // Replaces the arithmetic behind `MilvusClient.search`
 // (/root/reference/milvus/search_embeddings.py:15-22, /root/reference/milvus/RAG.py:383-390).
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -992,7 +993,7 @@ void avs_scratch_free(avs_store* s) {
     cudaFree(c.qf); cudaFree(c.qb); cudaFree(c.qnorm); cudaFree(c.eps_gemv); cudaFree(c.eps_gemm);
     cudaFree(c.cand); cudaFree(c.cnt); cudaFree(c.tau); cudaFree(c.topkeys); cudaFree(c.topn); cudaFree(c.status);
     cudaFree(c.out_s64); cudaFree(c.flagged); cudaFree(c.flagged2); cudaFree(c.dense_buf); cudaFree(c.rep_s); cudaFree(c.rep_row);
-    cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.rep_sel); cudaFree(c.rep_hist); cudaFree(c.gbar);
+    cudaFree(c.rep_cnt); cudaFree(c.rep_thr); cudaFree(c.rep_sel); cudaFree(c.rep_hist); cudaFree(c.gbar); cudaFree(c.trace);
     cudaFree(c.gather_send); cudaFree(c.gather_recv);
     cudaFree(c.d_ids);
     if (c.h2d_q) cudaFree(c.h2d_q);
@@ -1044,6 +1045,8 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.dense_buf, (size_t)(AVS_DENSE_MAX_NQ + 8) * AVS_DENSE_CAP));
         AVS_CHECK(dev_alloc(&c.rep_hist, (size_t)8 * 4096));
         AVS_CHECK(dev_alloc(&c.gbar, (size_t)4));
+        AVS_CHECK(dev_alloc(&c.trace, (size_t)64));
+        AVS_CUDA(cudaMemset(c.trace, 0, 64 * sizeof(u64)));
         AVS_CUDA(cudaMemset(c.gbar, 0, 4 * sizeof(unsigned int)));
     }
     c.nq_cap = nq2; c.kprime_cap = kp2; c.cap_cap = cap2; c.k_cap = k2;
@@ -1279,6 +1282,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         plan.bound = bound; plan.status = c.status; plan.eps = eps_used;
         plan.gbar = c.gbar + 0;
         plan.err = reinterpret_cast<unsigned int*>(s->dstat + 3);
+        plan.trace = s->opt_trace ? c.trace : nullptr;
         s->st_last_final_rows = rows_scanned < s->count ? rows_scanned : s->count;   // rows the timed launch scans
         size_t slot = 0;
         const bool timed = timing_begin(s, st, &slot);
@@ -1391,6 +1395,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
+    else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);
     else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;
     else if (k == "coarse_sigma") s->opt_coarse_sigma = value < 1 ? 1 : (int)value;
@@ -1411,6 +1416,14 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "p2p_timeouts") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_timeouts(s, out); }
     else if (k == "exchange_us") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_exchange_us(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
+    else if (k.rfind("trace:", 0) == 0) {      // phase timestamp i (ns, globaltimer) of the last persistent scan: synchronises
+        const int i = atoi(k.c_str() + 6);
+        if (i < 0 || i >= 64 || !s->sc.trace) { avs_set_error("avs_get_stat: trace slot out of range"); return AVS_E_INVALID; }
+        AVS_CUDA(cudaSetDevice(s->device));
+        u64 v = 0;
+        AVS_CUDA(cudaMemcpy(&v, s->sc.trace + i, sizeof(v), cudaMemcpyDeviceToHost));
+        *out = (int64_t)v;
+    }
     else if (k == "last_uncertified") *out = s->st_last_uncertified;   // of the last avs_search_host call; no device sync
     else if (k == "repaired_queries" || k == "uncertified_queries" || k == "wide_rescored_queries" || k == "barrier_timeouts") {
         AVS_CUDA(cudaSetDevice(s->device));

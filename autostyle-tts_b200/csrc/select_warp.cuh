@@ -75,6 +75,90 @@ __device__ __forceinline__ void wsel_emit_final(const WarpSelectArgs& a, int q, 
     a.status[q] |= st;
 }
 
+// Select among n_src <= 32 * EPL keys held in registers (key e in lane e % 32, register e / 32).  Every key's rank is
+// the number of keys above it (keys are distinct: the row index is part of the key; empty slots hold 0 and are skipped),
+// found by broadcasting the keys one by one: a short real loop instead of an unrolled sorting network - a lone warp
+// selecting for a single query runs ~10 instructions per key, not the ~6 k of a 256-key bitonic sort.  Writing key ->
+// slot[rank] leaves the survivors sorted.
+template <int EPL>
+__device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int lane, int jj, bool is_final, int dense_total,
+                                           int k_eps, const u64* src, int n_src, u64* c, int total_in, bool lost) {
+    u64 k[EPL];
+    int rk[EPL];
+    int nz = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int i = lane + 32 * r;
+        k[r] = i < n_src ? src[i] : 0ull;
+        rk[r] = 0;
+        nz += k[r] != 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    const int n_real = nz;
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int lim = n_src - 32 * r < 32 ? n_src - 32 * r : 32;      // uniform across the warp
+        for (int l = 0; l < lim; ++l) {
+            const u64 b = __shfl_sync(0xffffffffu, k[r], l);
+#pragma unroll
+            for (int r2 = 0; r2 < EPL; ++r2) rk[r2] += b > k[r2] ? 1 : 0;
+        }
+    }
+    // key of a given rank (0 when no such key): the one lane that holds it publishes it
+    auto key_of_rank = [&](int e) -> u64 {
+        u64 v = 0;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) v = (k[r] != 0ull && rk[r] == e) ? k[r] : v;
+        const unsigned who = __ballot_sync(0xffffffffu, v != 0ull);
+        return who ? __shfl_sync(0xffffffffu, v, __ffs(who) - 1) : 0ull;
+    };
+    __syncwarp();                                                      // every key has been read: `src` may alias `c`
+    if (!is_final) {
+        int keep = n_real >= jj ? jj : n_real;
+        u64 tau_new = n_real >= jj ? key_of_rank(jj - 1) : a.tau[q];
+        // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
+        if (k_eps > 0 && n_real >= k_eps && !lost) {
+            const u64 kk = key_of_rank(k_eps - 1);
+            const u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            if (t_eps < tau_new) {
+                tau_new = t_eps;
+                int above = 0;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) above += (k[r] >= tau_new && k[r] != 0ull) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+                keep = above;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < EPL; ++r)
+            if (k[r] != 0ull && rk[r] < keep) c[rk[r]] = k[r];
+        if (lane == 0) {
+            a.tau[q] = tau_new;
+            a.cnt[q] = keep;
+            if (lost) a.status[q] |= AVS_ST_OVERFLOW;
+        }
+    } else {
+        const int m = n_real < a.kprime ? n_real : a.kprime;
+        u64* tk = a.topkeys + (size_t)q * a.kprime;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            if (k[r] != 0ull) {
+                if (rk[r] < m) tk[rk[r]] = k[r];
+                c[rk[r]] = k[r];                                      // sorted and compacted: the wide-rescoring stage reads it
+            }
+        }
+        for (int i = m + lane; i < a.kprime; i += 32) tk[i] = 0ull;
+        const u64 key_kp = n_real >= a.kprime ? key_of_rank(a.kprime - 1) : 0ull;
+        if (lane == 0) {
+            a.cnt[q] = dense_total > 0 ? n_real : total_in;           // dense level: compacted, no empty slots left in front
+            wsel_emit_final(a, q, n_real, key_kp, lost);
+        }
+    }
+    __syncwarp();
+}
+
 // `list`: 256 u64 of shared memory owned by this warp (also used as a 256-bin int histogram by the radix path).
 __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, int lane, int j_rank, bool is_final,
                                                int dense_total, int k_eps, u64* list) {
@@ -92,12 +176,14 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
     int n_src = n;
     if (n > 256 && dense_total > 0 && !is_final && jj <= 32) {
         u64 lm = 0;
-        for (int i = lane; i < n; i += 32) { const u64 key = c[i]; lm = key > lm ? key : lm; }
+#pragma unroll 8
+        for (int i = lane; i < n; i += 32) { const u64 key = c[i]; lm = key > lm ? key : lm; }   // 8 loads in flight per lane
         u64 k1[1] = {lm};
         wsel_sort_desc<1>(k1, lane);
         const u64 P = __shfl_sync(0xffffffffu, k1[0], jj - 1);   // j distinct keys are >= P
         if (P != 0ull) {
             int m = 0;
+#pragma unroll 8
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
                 const u64 key = i < n ? c[i] : 0ull;
@@ -114,59 +200,11 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
     }
 
     if (n_src <= 256) {
-        // ---- everything fits 8 registers per lane: sort ----
-        u64 k8[8];
-        int nz = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int i = lane + 32 * r;
-            k8[r] = i < n_src ? src[i] : 0ull;
-            nz += k8[r] != 0ull;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-        wsel_sort_desc<8>(k8, lane);
-        const int n_real = nz;                                    // the dense level's padding slots hold key 0 and sort last
-        if (!is_final) {
-            int keep = n_real >= jj ? jj : n_real;
-            u64 tau_new = n_real >= jj ? wsel_pick<8>(k8, jj - 1) : a.tau[q];
-            // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
-            if (k_eps > 0 && n_real >= k_eps && !lost) {
-                const u64 kk = wsel_pick<8>(k8, k_eps - 1);
-                const u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
-                if (t_eps < tau_new) {
-                    tau_new = t_eps;
-                    int above = 0;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) above += (k8[r] >= tau_new && k8[r] != 0ull) ? 1 : 0;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
-                    keep = above;
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { const int i = lane + 32 * r; if (i < keep) c[i] = k8[r]; }
-            if (lane == 0) {
-                a.tau[q] = tau_new;
-                a.cnt[q] = keep;
-                if (lost) a.status[q] |= AVS_ST_OVERFLOW;
-            }
-        } else {
-            const int m = n_real < a.kprime ? n_real : a.kprime;
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = lane + 32 * r;
-                if (i < a.kprime) a.topkeys[(size_t)q * a.kprime + i] = i < m ? k8[r] : 0ull;
-                if (i < n) c[i] = k8[r];                          // sorted: the wide-rescoring stage reads it
-            }
-            const u64 key_kp = wsel_pick<8>(k8, a.kprime - 1 < 255 ? a.kprime - 1 : 255);
-            if (lane == 0) {
-                a.cnt[q] = dense_total > 0 ? n : total_in;
-                wsel_emit_final(a, q, n_real, key_kp, lost);
-            }
-        }
+        // ---- up to 8 keys per lane in registers: rank every key by counting ----
+        if (n_src <= 32) wsel_small<1>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
+        else if (n_src <= 64) wsel_small<2>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
+        else if (n_src <= 128) wsel_small<4>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
+        else wsel_small<8>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
         return;
     }
 

@@ -444,3 +444,121 @@ extern "C" int avs_get_ids(avs_store* s, int64_t first, int64_t n, int64_t* out,
     if (!dev) AVS_CUDA(cudaStreamSynchronize(st));
     return AVS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Bulk snapshot of a device store.  The reference's persistence is the Milvus Lite SQLite
+// file: one protobuf blob per row (/root/reference/milvus/RAG.py:541-544 writes 130 of them), which the drop-in keeps
+// for small collections (milvus_lite_db.py).  A 10^7-10^8-row store is saved raw instead:
+//   header (64 bytes) | ids [count] int64 | master rows [count, dim] fp32 exactly as inserted
+// The bf16 scan copy and the inverse norms are NOT stored: the normalise-on-insert kernel rebuilds them from the master
+// at HBM speed, far faster than reading another 50 % from disk, and bit-identically to the original insert.
+// Copies run through two pinned staging buffers so the PCIe transfer of one chunk overlaps the file I/O of the other.
+// ---------------------------------------------------------------------------------------------
+struct AvsSnapshotHeader {
+    char magic[8];            // "AVSSNAP1"
+    int32_t dim, metric;
+    int64_t count;
+    int64_t reserved[5];
+};
+static_assert(sizeof(AvsSnapshotHeader) == 64, "snapshot header is 64 bytes");
+#define AVS_SNAP_CHUNK ((size_t)64 << 20)
+
+static int snap_io_device(FILE* f, void* dev, size_t bytes, bool to_file, char* pin[2], cudaStream_t st[2], cudaEvent_t ev[2]) {
+    size_t off = 0;
+    int slot = 0;
+    size_t pending[2] = {0, 0}, pending_off[2] = {0, 0};
+    while (off < bytes || pending[0] || pending[1]) {
+        if (pending[slot]) {                       // finish what this slot started two chunks ago
+            AVS_CUDA(cudaEventSynchronize(ev[slot]));
+            if (to_file && fwrite(pin[slot], 1, pending[slot], f) != pending[slot]) { avs_set_error("snapshot: short write"); return AVS_E_INVALID; }
+            pending[slot] = 0;
+        }
+        if (off < bytes) {
+            const size_t n = bytes - off < AVS_SNAP_CHUNK ? bytes - off : AVS_SNAP_CHUNK;
+            if (to_file) {
+                AVS_CUDA(cudaMemcpyAsync(pin[slot], (char*)dev + off, n, cudaMemcpyDeviceToHost, st[slot]));
+            } else {
+                if (fread(pin[slot], 1, n, f) != n) { avs_set_error("snapshot: file is truncated"); return AVS_E_INVALID; }
+                AVS_CUDA(cudaMemcpyAsync((char*)dev + off, pin[slot], n, cudaMemcpyHostToDevice, st[slot]));
+            }
+            AVS_CUDA(cudaEventRecord(ev[slot], st[slot]));
+            pending[slot] = n; pending_off[slot] = off;
+            off += n;
+        }
+        slot ^= 1;
+    }
+    (void)pending_off;
+    return AVS_OK;
+}
+
+struct SnapIo {
+    char* pin[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    FILE* f = nullptr;
+    int open(const char* path, const char* mode) {
+        f = fopen(path, mode);
+        if (!f) { avs_set_error("snapshot: cannot open %s", path); return AVS_E_INVALID; }
+        return AVS_OK;
+    }
+    int device_init() {
+        for (int i = 0; i < 2; ++i) {
+            if (cudaHostAlloc((void**)&pin[i], AVS_SNAP_CHUNK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); avs_set_error("snapshot: out of pinned host memory"); return AVS_E_NOMEM; }
+            AVS_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            AVS_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        return AVS_OK;
+    }
+    ~SnapIo() {
+        for (int i = 0; i < 2; ++i) {
+            if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (pin[i]) cudaFreeHost(pin[i]);
+        }
+        if (f) fclose(f);
+        cudaGetLastError();
+    }
+};
+
+extern "C" int avs_save(avs_store* s, const char* path) {
+    if (!s || !path) { avs_set_error("avs_save: NULL argument"); return AVS_E_INVALID; }
+    SnapIo io;
+    AVS_CHECK(io.open(path, "wb"));
+    AVS_CUDA(cudaSetDevice(s->device));
+    AVS_CUDA(cudaDeviceSynchronize());
+    AVS_CHECK(io.device_init());
+    AvsSnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "AVSSNAP1", 8);
+    h.dim = s->dim; h.metric = s->metric; h.count = s->count;
+    if (fwrite(&h, sizeof(h), 1, io.f) != 1) { avs_set_error("snapshot: short write"); return AVS_E_INVALID; }
+    AVS_CHECK(snap_io_device(io.f, s->ids, (size_t)s->count * sizeof(int64_t), true, io.pin, io.st, io.ev));
+    AVS_CHECK(snap_io_device(io.f, s->master, (size_t)s->count * s->dim * sizeof(float), true, io.pin, io.st, io.ev));
+    if (fflush(io.f) != 0) { avs_set_error("snapshot: flush failed"); return AVS_E_INVALID; }
+    return AVS_OK;
+}
+
+extern "C" int avs_load(const char* path, int device, avs_store** out) {
+    if (!path || !out) { avs_set_error("avs_load: NULL argument"); return AVS_E_INVALID; }
+    *out = nullptr;
+    SnapIo io;
+    AVS_CHECK(io.open(path, "rb"));
+    AvsSnapshotHeader h;
+    if (fread(&h, sizeof(h), 1, io.f) != 1 || memcmp(h.magic, "AVSSNAP1", 8) != 0) { avs_set_error("avs_load: %s is not a store snapshot", path); return AVS_E_INVALID; }
+    if (h.dim <= 0 || h.dim > 32768 || h.count < 0 || h.count > 0xFFFFFFF0ll || (h.metric != AVS_METRIC_COSINE && h.metric != AVS_METRIC_IP)) {
+        avs_set_error("avs_load: corrupt snapshot header (dim %d, metric %d, count %lld)", h.dim, h.metric, (long long)h.count);
+        return AVS_E_INVALID;
+    }
+    avs_store* s = nullptr;
+    AVS_CHECK(avs_create(device, h.dim, h.metric, h.count, &s));
+    int rc = io.device_init();
+    if (rc == AVS_OK) rc = snap_io_device(io.f, s->ids, (size_t)h.count * sizeof(int64_t), false, io.pin, io.st, io.ev);
+    if (rc == AVS_OK) rc = snap_io_device(io.f, s->master, (size_t)h.count * h.dim * sizeof(float), false, io.pin, io.st, io.ev);
+    if (rc == AVS_OK && cudaDeviceSynchronize() != cudaSuccess) { avs_set_error("avs_load: device copy failed"); rc = AVS_E_CUDA; }
+    if (rc == AVS_OK) rc = launch_normalize(s, 0, h.count, 0);       // rebuilds the bf16 copy, the norms and the certificate's r_max
+    if (rc == AVS_OK && cudaDeviceSynchronize() != cudaSuccess) { avs_set_error("avs_load: normalise failed"); rc = AVS_E_CUDA; }
+    if (rc != AVS_OK) { avs_destroy(s); return rc; }
+    s->count = h.count;
+    *out = s;
+    return AVS_OK;
+}

@@ -25,7 +25,7 @@ METRIC_NAMES = {0: "COSINE", 1: "IP"}
 # every symbol include/avs.h declares; tests check the built library exports all of them
 ABI_SYMBOLS = (
     "avs_create", "avs_destroy", "avs_reserve", "avs_insert", "avs_fill_synthetic", "avs_count", "avs_dim",
-    "avs_metric", "avs_get_rows", "avs_get_ids", "avs_set_filter", "avs_search", "avs_search_host", "avs_nccl_unique_id",
+    "avs_metric", "avs_get_rows", "avs_get_ids", "avs_save", "avs_load", "avs_set_filter", "avs_search", "avs_search_host", "avs_nccl_unique_id",
     "avs_comm_init", "avs_search_sharded", "avs_search_sharded_host", "avs_p2p_init", "avs_p2p_connect", "avs_set_option", "avs_get_stat", "avs_scan_timing",
     "avs_last_error", "avs_version",
 )
@@ -70,6 +70,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "avs_metric": (i32, [vp]),
         "avs_get_rows": (i32, [vp, i64, i64, vp, vp]),
         "avs_get_ids": (i32, [vp, i64, i64, vp, vp]),
+        "avs_save": (i32, [vp, ctypes.c_char_p]),
+        "avs_load": (i32, [ctypes.c_char_p, i32, ctypes.POINTER(vp)]),
         "avs_set_filter": (i32, [vp, vp, i64]),
         "avs_search": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "avs_search_host": (i32, [vp, vp, i32, i32, vp, vp, vp]),
@@ -125,6 +127,21 @@ class Store:
         self.dim, self.metric, self.device = int(dim), metric, int(device)
         _check(self._lib, self._lib.avs_create(self.device, self.dim, METRIC_CODES[metric], int(capacity),
                                                ctypes.byref(self._h)))
+
+    # -- bulk snapshot ------------------------------------------------------------------------
+    def save(self, path: str):
+        """Raw snapshot (ids + fp32 master rows) for 10^7-10^8-row stores; see avs_save in include/avs.h."""
+        _check(self._lib, self._lib.avs_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "Store":
+        lib = load_library()
+        h = ctypes.c_void_p()
+        _check(lib, lib.avs_load(os.fsencode(path), int(device), ctypes.byref(h)))
+        self = cls.__new__(cls)
+        self._lib, self._h, self.device = lib, h, int(device)
+        self.dim, self.metric = int(lib.avs_dim(h)), METRIC_NAMES[int(lib.avs_metric(h))]
+        return self
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):

@@ -78,6 +78,13 @@ int avs_metric(const avs_store* s);
 int avs_get_rows(avs_store* s, int64_t first, int64_t n, float* out, void* stream);
 int avs_get_ids(avs_store* s, int64_t first, int64_t n, int64_t* out, void* stream);
 
+/* Bulk snapshot / restore of a device store (the reference's persistence is the Milvus Lite
+ * file re-opened by every script, /root/reference/milvus/search.py:197-210, one blob per row - kept for small collections
+ * by the Python layer).  File = 64-byte header | ids | fp32 master rows as inserted; the bf16 scan copy and the norms are
+ * rebuilt by the normalise-on-insert kernel on load.  Synchronous. */
+int avs_save(avs_store* s, const char* path);
+int avs_load(const char* path, int device, avs_store** out);
+
 /* Replaces `MilvusClient.search(collection_name, data=[vec,...], limit=k, ...)`
  * (/root/reference/milvus/search_embeddings.py:15-22, /root/reference/milvus/RAG.py:383-390,
  * /root/reference/milvus/search_json.py:247-254, /root/reference/src/search_milvus.py:139-146).

@@ -46,6 +46,20 @@ def test_no_cpu_fallback(pkg):
     assert c.search("t", data=[[1, 0, 0, 0]], limit=3) == [[]]            # empty collection: one empty list per query
 
 
+def test_snapshot_loader_rejects_garbage_without_a_gpu(pkg, tmp_path):
+    """avs_load validates the header before it touches the device: a wrong file is AVS_E_INVALID with a message."""
+    lib = pkg.load_library()
+    bad = tmp_path / "not_a_snapshot.avs"
+    bad.write_bytes(b"SQLite format 3\x00" + bytes(100))
+    out = ctypes.c_void_p()
+    assert lib.avs_load(os.fsencode(str(bad)), 0, ctypes.byref(out)) == -1 and b"not a store snapshot" in lib.avs_last_error()
+    assert lib.avs_load(os.fsencode(str(tmp_path / "missing.avs")), 0, ctypes.byref(out)) == -1
+    hdr = b"AVSSNAP1" + (0).to_bytes(4, "little") + (0).to_bytes(4, "little") + (5).to_bytes(8, "little") + bytes(40)
+    bad.write_bytes(hdr)
+    assert lib.avs_load(os.fsencode(str(bad)), 0, ctypes.byref(out)) == -1 and b"corrupt" in lib.avs_last_error()
+    assert lib.avs_save(None, b"x") == -1
+
+
 def test_schema_types_match_pymilvus_surface(pkg):
     DataType, FieldSchema, CollectionSchema = pkg.DataType, pkg.FieldSchema, pkg.CollectionSchema
     assert (DataType.INT64, DataType.VARCHAR, DataType.JSON, DataType.FLOAT_VECTOR) == (5, 21, 23, 101)

@@ -533,3 +533,41 @@ def test_many_queries_uncached_thresholds(pkg):
         assert st.stat("uncertified_queries") == 0
     finally:
         st.close()
+
+
+def test_snapshot_save_and_load_round_trip(pkg, tmp_path):
+    """raw snapshot of a device store; the restored store answers exactly like the original (the
+    bf16 copy / norms are rebuilt by K1 on load), also through MilvusClient.save_snapshot / load_snapshot with metadata."""
+    n, d, nq, k = 70_000, 96, 33, 10
+    X, ids, Q = _data(n, d, nq, seed=12)
+    st = pkg.Store(d, "COSINE", capacity=1024)
+    try:
+        st.insert(X[:30_000], ids[:30_000])
+        st.insert(X[30_000:], ids[30_000:])                       # two inserts: growth, then a snapshot of the grown store
+        want = st.search(Q, k, return_rows=True)
+        path = str(tmp_path / "store.avs")
+        st.save(path)
+        assert os.path.getsize(path) == 64 + n * 8 + n * d * 4
+        st2 = pkg.Store.load(path)
+        try:
+            assert len(st2) == n and st2.dim == d and st2.metric == "COSINE"
+            got = st2.search(Q, k, return_rows=True)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b)
+            assert np.array_equal(st2.get_rows(12_345, 7), X[12_345:12_352]) and np.array_equal(st2.get_ids(n - 3, 3), ids[n - 3:])
+            st2.insert(X[:5] * 2.0, np.arange(10 ** 9, 10 ** 9 + 5))          # a restored store keeps growing
+            assert len(st2) == n + 5
+        finally:
+            st2.close()
+    finally:
+        st.close()
+    c = pkg.MilvusClient(":memory:")
+    c.create_collection("snap", dimension=d)
+    c.insert("snap", [{"id": int(ids[i]), "vector": X[i], "file_id": f"f{i}.wav"} for i in range(2000)])
+    before = c.search("snap", data=Q[:4], limit=5, output_fields=["file_id"])
+    c.save_snapshot("snap", str(tmp_path / "coll.avs"))
+    c2 = pkg.MilvusClient(":memory:")
+    assert c2.load_snapshot(str(tmp_path / "coll.avs")) == "snap"
+    assert c2.search("snap", data=Q[:4], limit=5, output_fields=["file_id"]) == before
+    assert c2.get_collection_stats("snap")["row_count"] == 2000
+    c.close(); c2.close()
