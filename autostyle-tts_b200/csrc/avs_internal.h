@@ -188,6 +188,7 @@ struct avs_store {
     int opt_cta_group_small = 1;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
     int opt_dense_rows = AVS_DENSE_CAP;   // rows of the gemv path's threshold-free level (<= AVS_DENSE_CAP)
     int opt_hybrid = 1;              // auto mode, <= 8 queries: gemv dense level, tensor-core scan for the later levels
+    int opt_gemm_dense_rows = 2048;  // rows of the tensor-core path's threshold-free level (inside the candidate buffer)
     int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;

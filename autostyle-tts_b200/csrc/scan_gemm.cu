@@ -27,6 +27,8 @@
 // has not started; its spin is bounded all the same and a give-up is reported through `err`.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "avs_internal.h"
 #include "select_warp.cuh"
 
@@ -37,9 +39,14 @@ constexpr int BLOCK_N = 256;        // database rows per tile (== AVS_GROUP_ROWS
 constexpr int BLOCK_K = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
-constexpr int TAU_CACHE = 2048;         // thresholds of every query the CTA sweeps, cached in smem
-constexpr int STASH = 8;                // per-thread survivor stash (keys) between slot reservations
-static_assert(STASH == 8, "the dense level's transpose stages 32 queries x 8 keys in a warp's share of the stash");
+constexpr int TAU_CACHE = 1024;         // thresholds of the queries THIS CTA sweeps (128 per query block), cached in smem
+constexpr int STASH = 4;                // per-thread survivor stash (keys) between slot reservations
+constexpr int RAW = 2;                  // per-thread raw stash: qualifying 8-score groups of the current tile, expanded after
+                                        // the accumulator has been handed back to the MMA
+// per-warp share of the stash: [32 x STASH keys | 32 x RAW x 8 scores | 32 x RAW group codes]; the dense level's transpose
+// and the level select use its first 2 KB as scratch
+constexpr int WARP_STASH_BYTES = 32 * STASH * 8 + 32 * RAW * 32 + 32 * RAW * 2;
+static_assert(WARP_STASH_BYTES >= 2048 && WARP_STASH_BYTES % 16 == 0, "2 KB of scratch per warp, 16-byte aligned raw groups");
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -49,7 +56,8 @@ template <int CG> struct Cfg {
     static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = CG == 1 ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAU_CACHE * 8 + 256 * STASH * 8;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAU_CACHE * 8 + 8 * WARP_STASH_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -175,6 +183,33 @@ __device__ __forceinline__ void grid_barrier_epi(unsigned int* gbar, unsigned in
     epi_sync();
 }
 
+// Expands the parked groups of one thread (see the epilogue) into keys in its key stash; returns the new stash fill.
+// Survivors beyond the stash (duplicate-heavy data, dense accepts of the sparse levels) reserve their slots one by one
+// and go straight to the candidate buffer.  Out of line on purpose: five call sites, all off the hot path.
+__device__ __noinline__ int drain_raw(const float4* raw, const uint16_t* code_of, int n_raw, float tau_f,
+                                      const uint32_t* __restrict__ filt, int64_t row0, int valid_cols, u64* stash, int n_stash,
+                                      int* cnt_q, u64* cand_q, int cap) {
+    for (int e = 0; e < n_raw; ++e) {
+        const float4 lo4 = raw[2 * e], hi4 = raw[2 * e + 1];
+        const int code = code_of[e];
+        const int colb = (code >> 2) * 32 + (code & 3) * 8;          // first column of the group inside the tile half
+        const float g[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        uint32_t allow = 0xFFu;
+        if (filt) allow = (filt[(row0 + colb) >> 5] >> (colb & 31)) & 0xFFu;   // row filter: 8 bits of the chunk's bitmap word
+        const int vc = valid_cols - colb;                            // padding rows of the store's last group
+        allow = vc >= 8 ? allow : (vc <= 0 ? 0u : (allow & ((1u << vc) - 1)));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (g[i] >= tau_f && ((allow >> i) & 1u)) {
+                const u64 key = avs_make_key(g[i], (uint32_t)(row0 + colb + i));
+                if (n_stash < STASH) stash[n_stash++] = key;
+                else { const int pos = atomicAdd(cnt_q, 1); if (pos < cap) cand_q[pos] = key; }
+            }
+        }
+    }
+    return n_stash;
+}
+
 template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
@@ -191,7 +226,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
     u64* tau_smem = reinterpret_cast<u64*>(smem + C::STAGES * C::STAGE_BYTES + 256);
     u64* stash_smem = tau_smem + TAU_CACHE;
-    const int n_tau = n_qblocks * BLOCK_M * CG;
+    const int n_tau = n_qblocks * BLOCK_M;           // queries this CTA sweeps: 128 of every query block
     const bool tau_cached = n_tau <= TAU_CACHE;
     const u64* __restrict__ tau = plan.tau;
     u64* __restrict__ cand = plan.cand;
@@ -296,7 +331,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int ew = warp & 3;                       // TMEM lane quarter this warp may touch
         const int half = (warp - 4) >> 2;              // columns [half*128, half*128 + 128) of the tile
         uint32_t acc = 0, acc_phase = 0;
-        u64* const my_stash = stash_smem + (size_t)(threadIdx.x - 128) * STASH;
+        uint8_t* const warp_stash = reinterpret_cast<uint8_t*>(stash_smem) + (size_t)(warp - 4) * WARP_STASH_BYTES;
+        u64* const my_stash = reinterpret_cast<u64*>(warp_stash) + lane * STASH;
+        float4* const my_raw = reinterpret_cast<float4*>(warp_stash + 32 * STASH * 8) + lane * RAW * 2;
+        uint16_t* const my_code = reinterpret_cast<uint16_t*>(warp_stash + 32 * STASH * 8 + 32 * RAW * 32) + lane * RAW;
         // survivors of a tile wait in this thread's shared-memory stash; their slots in the query's candidate
         // buffer are reserved by ONE atomicAdd issued at the end of the tile and consumed a tile later, so the
         // L2 round trip of the atomic never stalls the warp
@@ -317,9 +355,14 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const AvsLevel& lv = plan.lv[l];
         const int64_t n_tiles = lv.n_visit * n_qblocks;
         if (tau_cached) {                              // this level's thresholds (the previous select wrote them)
-            for (int i = threadIdx.x - 128; i < n_tau; i += 256) tau_smem[i] = tau[i];
+            for (int i = threadIdx.x - 128; i < n_tau; i += 256)
+                tau_smem[i] = tau[((i / BLOCK_M) * CG + (int)cta_rank) * BLOCK_M + (i % BLOCK_M)];
             epi_sync();
         }
+        // the tile loop exists twice - threshold-free (dense) level and thresholded levels - so that the dense level's
+        // store code does not sit inside the hot loop of the thresholded levels
+        auto run_tiles = [&](auto dense_tag) {
+        constexpr bool DENSE = decltype(dense_tag)::value;
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
             const int64_t m = t / n_qblocks;
             const int qb = (int)(t - m * n_qblocks);
@@ -327,29 +370,51 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const bool has_pad = row0 + 128 > n_rows;  // only the last group of the store can hold padding rows
             const int valid_cols = has_pad ? (int)(n_rows > row0 ? n_rows - row0 : 0) : 128;
             const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;
-            const u64 tau_k = tau_cached ? tau_smem[q] : tau[q];
+            const u64 tau_k = tau_cached ? tau_smem[qb * BLOCK_M + ew * 32 + lane] : tau[q];
             const float tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k);  // NaN for padding slots: never accepts
             u64* const my_cand = cand + (size_t)q * cap;
             flush_pending();
-            int n_stash = 0;
+            int n_stash = 0, n_raw = 0;
             auto reserve = [&]() {
                 pend_n = n_stash;
                 pend_dst = my_cand;
                 pend_pos = atomicAdd(cnt + q, n_stash);   // result is first touched by flush_pending()
                 n_stash = 0;
             };
+            // Accepts are rare and hit ONE lane of a warp: whatever that lane does, the other 31 wait, and the tile's
+            // accumulator is not handed back to the MMA before the slowest of the 16 epilogue warps is through
+            // (measured: ~3 k cycles per accept when the survivors were expanded in place).  So the hot path only parks
+            // a qualifying group of 8 scores in the thread's raw stash (three shared-memory stores); drain_raw() turns
+            // the parked groups into keys AFTER the hand-back, off the MMA's critical path.
+            auto drain = [&]() {
+                n_stash = drain_raw(my_raw, my_code, n_raw, tau_f, filt, row0, valid_cols, my_stash, n_stash, cnt + q, my_cand, cap);
+                n_raw = 0;
+            };
             // 32 scores of this thread's query.  Dense level (threshold-free, the sparsest level): every score goes
             // to its own slot, no atomics.  Otherwise 4 independent group maxima (short dependency chains) and ONE
             // compare against the threshold; only a qualifying chunk builds the bit mask of its survivors.
             auto process = [&](const uint32_t (&v)[32], int col0) {
-                if (lv.dense) {
+                if constexpr (DENSE) {
                     // A lane owns one query's 32 scores, and the query's keys are contiguous in memory: stored lane by
                     // lane, every store instruction would touch 32 sectors for 8 bytes each (1 K LSU transactions per
                     // warp and chunk; the 2 048-row level cost 36 us that way).  So the warp transposes 32 queries x 8
                     // keys at a time through its 2 KB of the (idle) survivor stash, XOR-swizzled so that neither side
                     // has bank conflicts, and stores 4 queries x 64 contiguous bytes per instruction.
                     const uint32_t allow = filt ? filt[(row0 + col0) >> 5] : ~0u;   // the chunk's 32 rows = one bitmap word
-                    u64* const stage = stash_smem + (size_t)(warp - 4) * 32 * STASH;
+                    const int live_lanes = plan.nq - (q - lane);                    // real queries among this warp's 32 lanes
+                    if (live_lanes <= 8) {
+                        // a handful of queries (the reference's batch-1 search): the live lanes store their 32 keys
+                        // themselves - 32 narrow stores instead of the 16-step transpose through shared memory
+                        if (lane < live_lanes) {
+                            u64* const gq = cand + (size_t)q * cap + (size_t)m * BLOCK_N + half * 128 + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                gq[i] = (col0 + i < valid_cols && ((allow >> i) & 1u))
+                                            ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
+                        }
+                        return;
+                    }
+                    u64* const stage = reinterpret_cast<u64*>(warp_stash);
                     const int rq = lane >> 3, rc = lane & 7;                       // reader role: query 4j + rq, key rc of the slice
                     u64* const gbase = cand + (size_t)(q - lane) * cap + (size_t)m * BLOCK_N + half * 128 + col0;
                     const bool live = q < plan.nq;                                 // padding query slots keep empty keys
@@ -360,17 +425,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             const int i = 8 * sl + c;
                             const u64 key = (col0 + i < valid_cols && live && ((allow >> i) & 1u))
                                                 ? avs_make_key(__uint_as_float(v[i]), (uint32_t)(row0 + col0 + i)) : 0ull;
-                            stage[lane * STASH + (c ^ ((lane >> 1) & 7))] = key;
+                            stage[lane * 8 + (c ^ ((lane >> 1) & 7))] = key;
                         }
                         __syncwarp();
                         u64* gp = gbase + (size_t)rq * cap + 8 * sl + rc;
 #pragma unroll 1
                         for (int r = rq; r < 32; r += 4, gp += (size_t)4 * cap)   // kept rolled: the kernel sits at its register limit
-                            *gp = stage[r * STASH + (rc ^ ((r >> 1) & 7))];
+                            *gp = stage[r * 8 + (rc ^ ((r >> 1) & 7))];
                         __syncwarp();
                     }
                     return;
-                }
+                } else {
                 float gm[4];
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
@@ -380,43 +445,19 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
                 if (mx >= tau_f) {
-                    uint32_t mask = 0;                 // survivors, looked for only inside the groups that qualify
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {
-                        if (gm[gi] >= tau_f) {
-                            uint32_t mg = 0;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) mg |= (__uint_as_float(v[8 * gi + i]) >= tau_f ? 1u : 0u) << i;
-                            mask |= mg << (8 * gi);
+                        if (gm[gi] >= tau_f) {             // park the group: 8 scores + where they sit
+                            if (n_raw == RAW) drain();     // a third qualifying group in one tile (dense accepts of the sparse levels)
+                            my_raw[2 * n_raw] = make_float4(__uint_as_float(v[8 * gi]), __uint_as_float(v[8 * gi + 1]),
+                                                            __uint_as_float(v[8 * gi + 2]), __uint_as_float(v[8 * gi + 3]));
+                            my_raw[2 * n_raw + 1] = make_float4(__uint_as_float(v[8 * gi + 4]), __uint_as_float(v[8 * gi + 5]),
+                                                                __uint_as_float(v[8 * gi + 6]), __uint_as_float(v[8 * gi + 7]));
+                            my_code[n_raw] = (uint16_t)((col0 >> 5) * 4 + gi);
+                            ++n_raw;
                         }
                     }
-                    if (has_pad) {
-                        const int vc = valid_cols - col0;
-                        mask = vc >= 32 ? mask : (vc <= 0 ? 0u : (mask & ((1u << vc) - 1)));
-                    }
-                    if (filt) mask &= filt[(row0 + col0) >> 5];      // row filter: the chunk's 32 rows = one bitmap word
-                    while (mask) {                     // more than STASH survivors (duplicate-heavy data): drain in rounds
-                        uint32_t sub = mask;
-                        if (n_stash + __popc(mask) > STASH) {
-                            if (n_stash) { reserve(); flush_pending(); }
-                            sub = 0;
-                            uint32_t rest = mask;
-                            for (int b = 0; b < STASH && rest; ++b) { sub |= rest & (0u - rest); rest &= rest - 1; }
-                        }
-                        mask &= ~sub;
-#pragma unroll
-                        for (int gi = 0; gi < 4; ++gi) {
-                            if ((sub >> (8 * gi)) & 0xFFu) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if ((sub >> (8 * gi + i)) & 1) {
-                                        my_stash[n_stash] = avs_make_key(__uint_as_float(v[8 * gi + i]), (uint32_t)(row0 + col0 + 8 * gi + i));
-                                        ++n_stash;
-                                    }
-                                }
-                            }
-                        }
-                    }
+                }
                 }
             };
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
@@ -446,17 +487,24 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
             }
             process(vb, 96);
+            if (n_raw) drain();
             if (n_stash) reserve();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        };
+        if (lv.dense) run_tiles(std::true_type{}); else run_tiles(std::false_type{});
         flush_pending();
         stamp(1 + 4 * l);                              // this CTA's tiles of the level are done
+        if (plan.trace != nullptr && threadIdx.x == 128 && blockIdx.x < 256) {   // per-CTA finish time of the level (load balance)
+            u64 tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
+            plan.trace[64 + l * 256 + blockIdx.x] = tn;
+        }
         // ---- level done on this CTA: wait for the whole grid, then select (warp per query), then the next level ----
         grid_barrier_epi(plan.gbar, epoch, plan.err);
         stamp(2 + 4 * l);                              // the whole grid has finished the level
         {
             const bool final_level = plan.last_is_final && l == plan.n_levels - 1;
-            u64* const list = stash_smem + (size_t)(warp - 4) * 256;           // 2 KB of the (now idle) survivor stash per warp
+            u64* const list = reinterpret_cast<u64*>(warp_stash);             // 2 KB of the (now idle) survivor stash of this warp
             const int dense_total = lv.dense ? (int)(lv.n_visit * AVS_GROUP_ROWS) : 0;
             for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
                 warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);

@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
 // row and of the query in flight per lane before the first FMA); the scalar path keeps the same order and
 // therefore the same bits.  Used by both rescoring and repair.
 // ---------------------------------------------------------------------------------------------
-#define AVS_XS_UNROLL 2
+#define AVS_XS_UNROLL 4
 __device__ __forceinline__ double exact_score(const float* __restrict__ x, const float* __restrict__ q, int dim,
                                               double qn, int metric, int lane) {
     double dot = 0.0, xx = 0.0;
@@ -1045,8 +1045,8 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.dense_buf, (size_t)(AVS_DENSE_MAX_NQ + 8) * AVS_DENSE_CAP));
         AVS_CHECK(dev_alloc(&c.rep_hist, (size_t)8 * 4096));
         AVS_CHECK(dev_alloc(&c.gbar, (size_t)4));
-        AVS_CHECK(dev_alloc(&c.trace, (size_t)64));
-        AVS_CUDA(cudaMemset(c.trace, 0, 64 * sizeof(u64)));
+        AVS_CHECK(dev_alloc(&c.trace, (size_t)64 + AVS_MAX_LEVELS * 256 * 9));
+        AVS_CUDA(cudaMemset(c.trace, 0, (64 + AVS_MAX_LEVELS * 256 * 9) * sizeof(u64)));
         AVS_CUDA(cudaMemset(c.gbar, 0, 4 * sizeof(unsigned int)));
     }
     c.nq_cap = nq2; c.kprime_cap = kp2; c.cap_cap = cap2; c.k_cap = k2;
@@ -1154,7 +1154,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // the threshold-free level: <= 2048 rows inside the candidate buffer on the tensor-core path; the gemv path (few
     // queries) stores up to 64 K rows densely in its own buffer, which saves it a whole intermediate level
     const bool dense_gemv = !use_gemm && nq <= AVS_DENSE_MAX_NQ;
-    const int64_t level0_rows = dense_gemv ? s->opt_dense_rows : (cap < 2048 ? cap : 2048);
+    const int64_t level0_rows = dense_gemv ? s->opt_dense_rows : (cap < s->opt_gemm_dense_rows ? cap : s->opt_gemm_dense_rows);
     while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
         // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
         // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
@@ -1396,6 +1396,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
+    else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));
     else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);
     else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;
     else if (k == "coarse_sigma") s->opt_coarse_sigma = value < 1 ? 1 : (int)value;
@@ -1418,7 +1419,7 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k.rfind("trace:", 0) == 0) {      // phase timestamp i (ns, globaltimer) of the last persistent scan: synchronises
         const int i = atoi(k.c_str() + 6);
-        if (i < 0 || i >= 64 || !s->sc.trace) { avs_set_error("avs_get_stat: trace slot out of range"); return AVS_E_INVALID; }
+        if (i < 0 || i >= 64 + AVS_MAX_LEVELS * 256 * 9 || !s->sc.trace) { avs_set_error("avs_get_stat: trace slot out of range"); return AVS_E_INVALID; }
         AVS_CUDA(cudaSetDevice(s->device));
         u64 v = 0;
         AVS_CUDA(cudaMemcpy(&v, s->sc.trace + i, sizeof(v), cudaMemcpyDeviceToHost));

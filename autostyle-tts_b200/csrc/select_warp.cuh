@@ -201,9 +201,12 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
 
     if (n_src <= 256) {
         // ---- up to 8 keys per lane in registers: rank every key by counting ----
+        // the rank loop costs n_src * (2 + 3 * EPL) instructions: registers per lane follow the key count closely
         if (n_src <= 32) wsel_small<1>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
         else if (n_src <= 64) wsel_small<2>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
+        else if (n_src <= 96) wsel_small<3>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
         else if (n_src <= 128) wsel_small<4>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
+        else if (n_src <= 192) wsel_small<6>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
         else wsel_small<8>(a, q, lane, jj, is_final, dense_total, k_eps, src, n_src, c, total_in, lost);
         return;
     }

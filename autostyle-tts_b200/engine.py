@@ -239,8 +239,9 @@ class Store:
                                                     rows.ctypes.data))
         unproven = self.stat("last_uncertified")
         if unproven:
-            warnings.warn(f"{unproven} of {nq} queries have more than 4096 rows tied with their k-th score: the hits returned "
-                          "for them are best matches, but the tie order by primary key is not proven", ExactnessWarning)
+            warnings.warn(f"{unproven} of {nq} queries could not be proven exact: more rows than the exact-repair slice holds "
+                          "(up to 4096) score within 2^-15 of their k-th best (masses of duplicate rows). The hits returned for "
+                          "them are the best found, but may differ from the exact top-k in the tied tail", ExactnessWarning)
         return (ids, sc, rows) if return_rows else (ids, sc)
 
     def set_filter(self, mask):

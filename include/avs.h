@@ -143,8 +143,13 @@ int avs_set_option(avs_store* s, const char* key, int64_t value);
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
  * "uncertified_queries", "p2p_timeouts", "exchange_us" (mean duration of the peer-memory exchange kernel while
  * avs_scan_timing is on), "last_kprime", "last_levels", "last_scan_path", "last_final_rows";
- * "last_uncertified": queries of the last avs_search_host call whose top-k could not be proven exact (more than 4096
- * rows tied with the k-th score) - read without a device synchronisation. */
+ * "barrier_timeouts" (a grid barrier of a persistent kernel gave up: must stay 0);
+ * "last_uncertified": queries of the last avs_search_host call whose top-k could not be proven exact - read without a
+ * device synchronisation.  Every query whose certificate fails is settled by the exact float64 repair (all of them, in
+ * groups; a query without a usable lower bound gets one from a histogram search).  A query is left uncertified only when
+ * more rows than its repair slice holds (4096, or pool / flagged-queries if thousands of queries fail at once, never
+ * fewer than 256) have scores within 2^-15 relative of its k-th best - masses of (near-)duplicate rows.  Its hits are then
+ * the best found by the earlier stages: possibly not the exact top-k, and reported, never silent. */
 int avs_get_stat(avs_store* s, const char* key, int64_t* out);
 
 /* Timing hook for bench.py: when enabled, CUDA events bracket the dominant scan

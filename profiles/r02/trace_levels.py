@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--metric", default="COSINE")
     ap.add_argument("--batches", default="1,8,128,1024")
     ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--per-cta", action="store_true", help="add the distribution of per-CTA finish times per level")
     a = ap.parse_args()
     pkg = importlib.import_module("autostyle-tts_b200")
     synth = importlib.import_module("autostyle-tts_b200.synth")
@@ -52,6 +53,28 @@ def main():
             s0, s1, s2, s3, s4 = t[4 * l], t[4 * l + 1], t[4 * l + 2], t[4 * l + 3], t[4 * l + 4]
             rows.append({"level": l, "scan_us": (s1 - s0) / 1e3, "wait_grid_us": (s2 - s1) / 1e3, "select_us": (s3 - s2) / 1e3,
                          "wait_thresholds_us": (s4 - s3) / 1e3})
+        if a.per_cta:
+            for l in range(n_lv):
+                fin = np.array([st.stat(f"trace:{64 + l * 256 + c}") for c in range(148)], dtype=np.float64)
+                fin = fin[fin > 0]
+                if fin.size:
+                    rel = (fin - t[4 * l]) / 1e3
+                    order = np.argsort(rel)
+                    rows[l]["cta_finish_us"] = {"min": float(rel.min()), "p25": float(np.percentile(rel, 25)), "median": float(np.median(rel)),
+                                                "p75": float(np.percentile(rel, 75)), "max": float(rel.max()), "ctas": int(fin.size),
+                                                "slowest_ctas": [int(x) for x in order[-6:]], "fastest_ctas": [int(x) for x in order[:6]],
+                                                "even_median": float(np.median(rel[0::2])), "odd_median": float(np.median(rel[1::2]))}
+                # epilogue accounting (cycles, warp 4 and warp 11 of a few CTAs): waiting for the accumulator, tfull -> tempty
+                # arrive (the part the MMA can wait for), arrive -> end of tile
+                base = 64 + 12 * 256
+                acc = []
+                for cta in (0, 1, 2, 3, 40, 41, 100, 101):
+                    for w in (0, 4):
+                        v = [st.stat(f"trace:{base + (l * 256 + cta) * 8 + w + i}") for i in range(4)]
+                        if v[3]:
+                            acc.append({"cta": cta, "warp": 4 if w == 0 else 11, "tiles": v[3], "wait_cyc_per_tile": v[0] / v[3],
+                                        "crit_cyc_per_tile": v[1] / v[3], "tail_cyc_per_tile": v[2] / v[3]})
+                rows[l]["epilogue_cycles"] = acc
         out.append({"batch": b, "ms_per_search": e0.elapsed_time(e1) / 20, "levels_total": L, "levels_in_persistent_kernel": n_lv,
                     "kernel_us": (t[4 * n_lv] - t[0]) / 1e3 if n_lv else None, "per_level": rows})
     print(json.dumps({"rows": a.rows, "dim": a.dim, "k": a.k, "opts": a.opt, "trace": out}))

