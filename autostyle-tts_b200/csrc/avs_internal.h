@@ -189,6 +189,7 @@ struct avs_store {
     int opt_dense_rows = AVS_DENSE_CAP;   // rows of the gemv path's threshold-free level (<= AVS_DENSE_CAP)
     int opt_hybrid = 1;              // auto mode, <= 8 queries: gemv dense level, tensor-core scan for the later levels
     int opt_gemm_dense_rows = 2048;  // rows of the tensor-core path's threshold-free level (inside the candidate buffer)
+    int opt_finalize_threads = 0;    // 0: 1024 threads per query up to 64 queries, 256 beyond
     int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int rank = 0, world = 1;

@@ -429,7 +429,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         }
                         __syncwarp();
                         u64* gp = gbase + (size_t)rq * cap + 8 * sl + rc;
-#pragma unroll 1
+#pragma unroll 4
                         for (int r = rq; r < 32; r += 4, gp += (size_t)4 * cap)   // kept rolled: the kernel sits at its register limit
                             *gp = stage[r * 8 + (rc ^ ((r >> 1) & 7))];
                         __syncwarp();
@@ -506,8 +506,14 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const bool final_level = plan.last_is_final && l == plan.n_levels - 1;
             u64* const list = reinterpret_cast<u64*>(warp_stash);             // 2 KB of the (now idle) survivor stash of this warp
             const int dense_total = lv.dense ? (int)(lv.n_visit * AVS_GROUP_ROWS) : 0;
-            for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
-                warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);
+            if (plan.nq <= (int)gridDim.x) {           // at most one query per CTA: its 8 epilogue warps share the select
+                if ((int)blockIdx.x < plan.nq)
+                    cta_select_level(plan, (int)blockIdx.x, warp - 4, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l],
+                                     stash_smem, []() { epi_sync(); });
+            } else {
+                for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
+                    warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);
+            }
         }
         stamp(3 + 4 * l);                              // this CTA's share of the selects is done
         if (l + 1 < plan.n_levels) grid_barrier_epi(plan.gbar, epoch, plan.err);

@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(1024) select_level_kernel(SelectArgs a) {
 // row and of the query in flight per lane before the first FMA); the scalar path keeps the same order and
 // therefore the same bits.  Used by both rescoring and repair.
 // ---------------------------------------------------------------------------------------------
-#define AVS_XS_UNROLL 4
+#define AVS_XS_UNROLL 2
 __device__ __forceinline__ double exact_score(const float* __restrict__ x, const float* __restrict__ q, int dim,
                                               double qn, int metric, int lane) {
     double dot = 0.0, xx = 0.0;
@@ -1290,7 +1290,8 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         if (timed) timing_end(s, st, slot);
     }
 
-    finalize_kernel<<<nq, nq <= 64 ? 1024 : 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
+    const int fin_threads = s->opt_finalize_threads > 0 ? s->opt_finalize_threads : (nq <= 64 ? 1024 : 256);
+    finalize_kernel<<<nq, fin_threads, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
                                         n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
                                         c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
     s->st_launches++;
@@ -1396,6 +1397,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
+    else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));
     else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);
     else if (k == "fine_min_batch") s->opt_fine_min_batch = value < 1 ? 1 : (int)value;

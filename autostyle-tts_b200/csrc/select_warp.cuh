@@ -80,31 +80,10 @@ __device__ __forceinline__ void wsel_emit_final(const WarpSelectArgs& a, int q, 
 // found by broadcasting the keys one by one: a short real loop instead of an unrolled sorting network - a lone warp
 // selecting for a single query runs ~10 instructions per key, not the ~6 k of a 256-key bitonic sort.  Writing key ->
 // slot[rank] leaves the survivors sorted.
+// Output phase of the small selects: k[] = the keys (key e in lane e % 32, register e / 32), rk[] = their ranks.
 template <int EPL>
-__device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int lane, int jj, bool is_final, int dense_total,
-                                           int k_eps, const u64* src, int n_src, u64* c, int total_in, bool lost) {
-    u64 k[EPL];
-    int rk[EPL];
-    int nz = 0;
-#pragma unroll
-    for (int r = 0; r < EPL; ++r) {
-        const int i = lane + 32 * r;
-        k[r] = i < n_src ? src[i] : 0ull;
-        rk[r] = 0;
-        nz += k[r] != 0ull;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-    const int n_real = nz;
-#pragma unroll
-    for (int r = 0; r < EPL; ++r) {
-        const int lim = n_src - 32 * r < 32 ? n_src - 32 * r : 32;      // uniform across the warp
-        for (int l = 0; l < lim; ++l) {
-            const u64 b = __shfl_sync(0xffffffffu, k[r], l);
-#pragma unroll
-            for (int r2 = 0; r2 < EPL; ++r2) rk[r2] += b > k[r2] ? 1 : 0;
-        }
-    }
+__device__ __forceinline__ void wsel_emit(const WarpSelectArgs& a, int q, int lane, const u64 (&k)[EPL], const int (&rk)[EPL], int n_real,
+                                          int jj, bool is_final, int dense_total, int k_eps, u64* c, int total_in, bool lost) {
     // key of a given rank (0 when no such key): the one lane that holds it publishes it
     auto key_of_rank = [&](int e) -> u64 {
         u64 v = 0;
@@ -113,7 +92,6 @@ __device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int l
         const unsigned who = __ballot_sync(0xffffffffu, v != 0ull);
         return who ? __shfl_sync(0xffffffffu, v, __ffs(who) - 1) : 0ull;
     };
-    __syncwarp();                                                      // every key has been read: `src` may alias `c`
     if (!is_final) {
         int keep = n_real >= jj ? jj : n_real;
         u64 tau_new = n_real >= jj ? key_of_rank(jj - 1) : a.tau[q];
@@ -157,6 +135,39 @@ __device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int l
         }
     }
     __syncwarp();
+}
+
+// Select among n_src <= 32 * EPL keys held in registers (key e in lane e % 32, register e / 32).  Every key's rank is
+// the number of keys above it (keys are distinct: the row index is part of the key; empty slots hold 0 and are skipped),
+// found by broadcasting the keys one by one: a short real loop instead of an unrolled sorting network - a lone warp
+// selecting for a single query runs ~10 instructions per key, not the ~6 k of a 256-key bitonic sort.  Writing key ->
+// slot[rank] leaves the survivors sorted.
+template <int EPL>
+__device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int lane, int jj, bool is_final, int dense_total,
+                                           int k_eps, const u64* src, int n_src, u64* c, int total_in, bool lost) {
+    u64 k[EPL];
+    int rk[EPL];
+    int nz = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int i = lane + 32 * r;
+        k[r] = i < n_src ? src[i] : 0ull;
+        rk[r] = 0;
+        nz += k[r] != 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int lim = n_src - 32 * r < 32 ? n_src - 32 * r : 32;      // uniform across the warp
+        for (int l = 0; l < lim; ++l) {
+            const u64 b = __shfl_sync(0xffffffffu, k[r], l);
+#pragma unroll
+            for (int r2 = 0; r2 < EPL; ++r2) rk[r2] += b > k[r2] ? 1 : 0;
+        }
+    }
+    __syncwarp();                                                      // every key has been read: `src` may alias `c`
+    wsel_emit<EPL>(a, q, lane, k, rk, nz, jj, is_final, dense_total, k_eps, c, total_in, lost);
 }
 
 // `list`: 256 u64 of shared memory owned by this warp (also used as a 256-bin int histogram by the radix path).
@@ -297,4 +308,194 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
         }
     }
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few queries (at most one per CTA - the reference's batch-1 search): the 8 epilogue warps of a CTA select for ONE query
+// together instead of leaving it to a lone warp whose latency the whole grid waits for.  Same results as
+// warp_select_level; the rank counting (the n^2 part) and the dense level's slot scan are split 8 ways.
+//   `scratch`: >= 5.5 KB of shared memory of the CTA, idle during the select; sync() = barrier of the 8 warps.
+// Every one of the 8 warps must call this (uniform control flow: the barriers are inside).
+// ---------------------------------------------------------------------------------------------
+template <typename SyncFn>
+__device__ __noinline__ void cta_select_level(const WarpSelectArgs& a, int q, int w, int lane, int j_rank, bool is_final,
+                                              int dense_total, int k_eps, u64* scratch, SyncFn sync) {
+    u64* const list = scratch;                                       // [256] compacted keys of the dense level
+    u64* const maxima = scratch + 256;                               // [256] lane maxima of the 8 warps
+    int* const ranks = reinterpret_cast<int*>(scratch + 512);        // [256]
+    int* const misc = ranks + 256;                                   // [0] list fill, [1] fallback flag
+    u64* const pivot = scratch + 512 + 160;                          // [1]
+    u64* c = a.cand + (size_t)q * a.cap;
+    const int total_in = dense_total > 0 ? dense_total : a.cnt[q];
+    const bool lost = dense_total == 0 && total_in > a.cap;
+    const int n = total_in < a.cap ? total_in : a.cap;
+    int jj = j_rank;
+    if (lost) { jj = (int)(((long long)j_rank * a.cap) / total_in); if (jj < 1) jj = 1; }
+    const u64* src = c;
+    int n_src = n;
+    const int tid = w * 32 + lane;
+    if (tid < 256) ranks[tid] = 0;
+    if (tid == 0) { misc[0] = 0; misc[1] = 0; *pivot = 0ull; }
+    sync();
+
+    // ---- dense level, small rank: pivot = rank-j value of the 256 lane maxima, each warp scanning an eighth of the slots ----
+    if (n > 256 && n <= 2048 && dense_total > 0 && !is_final && jj <= 32) {
+        u64 mine[8];
+        u64 lm = 0;
+        const int per = (n + 7) >> 3, lo = w * per, hi = lo + per < n ? lo + per : n;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = lo + lane + 32 * r;
+            mine[r] = i < hi ? c[i] : 0ull;
+            lm = mine[r] > lm ? mine[r] : lm;
+        }
+        maxima[tid] = lm;
+        sync();
+        u64 k[8];
+        int rk[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { k[r] = maxima[lane + 32 * r]; rk[r] = 0; }
+        {   // this warp counts against the maxima of register w
+            u64 kw = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) kw = r == w ? k[r] : kw;
+            for (int l = 0; l < 32; ++l) {
+                const u64 b = __shfl_sync(0xffffffffu, kw, l);
+#pragma unroll
+                for (int r2 = 0; r2 < 8; ++r2) rk[r2] += b > k[r2] ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (rk[r]) atomicAdd(&ranks[lane + 32 * r], rk[r]);
+        sync();
+        // equal maxima (several lanes without a key: 0) share a rank; the rank-(jj-1) one, if it is a real key, is the pivot
+        if (w == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (k[r] != 0ull && ranks[lane + 32 * r] == jj - 1) *pivot = k[r];
+        }
+        sync();
+        const u64 P = *pivot;
+        if (P != 0ull) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (mine[r] >= P) { const int pos = atomicAdd(&misc[0], 1); if (pos < 256) list[pos] = mine[r]; }
+        }
+        if (tid < 256) ranks[tid] = 0;
+        sync();
+        const int m = misc[0];
+        if (P != 0ull && m <= 256) { src = list; n_src = m; }         // m >= jj by construction
+    }
+
+    if (n_src <= 256) {
+        u64 k[8];
+        int rk[8];
+        int nz = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = lane + 32 * r;
+            k[r] = i < n_src ? src[i] : 0ull;
+            rk[r] = 0;
+            nz += k[r] != 0ull;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        const int lim = n_src - 32 * w < 32 ? n_src - 32 * w : 32;   // this warp broadcasts the keys of register w
+        if (lim > 0) {
+            u64 kw = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) kw = r == w ? k[r] : kw;
+            for (int l = 0; l < lim; ++l) {
+                const u64 b = __shfl_sync(0xffffffffu, kw, l);
+#pragma unroll
+                for (int r2 = 0; r2 < 8; ++r2) rk[r2] += b > k[r2] ? 1 : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (rk[r]) atomicAdd(&ranks[lane + 32 * r], rk[r]);
+        }
+        sync();                                                       // all partial ranks are in; every warp has read `src`
+        if (w == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) rk[r] = ranks[lane + 32 * r];
+            wsel_emit<8>(a, q, lane, k, rk, nz, jj, is_final, dense_total, k_eps, c, total_in, lost);
+        }
+    } else {
+        // ---- large sets: 8-pass byte-wise radix select, the 8 warps histogramming an eighth of the keys each ----
+        int* const hist = ranks;                                      // 256 bins
+        {
+            int nzc = 0;
+            for (int i = tid; i < n; i += 256) nzc += c[i] != 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
+            if (lane == 0 && nzc) atomicAdd(&misc[1], nzc);
+        }
+        sync();
+        const int n_real = misc[1];
+        const int want = is_final ? (n_real < a.kprime ? n_real : a.kprime) : (n_real >= jj ? jj : n_real);
+        u64 prefix = 0, maskb = 0;
+        int rank = want - 1;
+        if (want > 0) {
+            for (int byte = 7; byte >= 0; --byte) {
+                if (tid < 256) hist[tid] = 0;
+                sync();
+                for (int i0 = 0; i0 < n; i0 += 256) {                 // whole warps stay converged for the match below
+                    const int i = i0 + tid;
+                    const u64 key = i < n ? c[i] : 0ull;
+                    const bool in = i < n && key != 0ull && (key & maskb) == prefix;
+                    const int bin = in ? (int)((key >> (8 * byte)) & 0xFFull) : 256 + lane;
+                    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                    if (in && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+                }
+                sync();
+                if (w == 0) {                                         // lane l owns bins 255-8l .. 248-8l (descending key order)
+                    int loc[8], sum = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) { loc[b] = hist[255 - 8 * lane - b]; sum += loc[b]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+                    int accb = incl - sum;
+                    if (rank >= accb && rank < incl) {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            if (rank >= accb && rank < accb + loc[b]) { misc[2] = 255 - 8 * lane - b; misc[3] = accb; }
+                            accb += loc[b];
+                        }
+                    }
+                }
+                sync();
+                prefix |= (u64)misc[2] << (8 * byte);
+                maskb |= 0xFFull << (8 * byte);
+                rank -= misc[3];
+            }
+        }
+        const u64 Pk = want > 0 ? prefix : ~0ull;                      // exactly `want` keys are >= it
+        if (tid == 0) misc[0] = 0;
+        sync();
+        if (!is_final) {
+            // survivors (at most 256: the ranks are clamped) go through the shared list, then to the front of the buffer
+            for (int i = tid; i < n; i += 256) {
+                const u64 key = c[i];
+                if (key >= Pk && key != 0ull) { const int pos = atomicAdd(&misc[0], 1); if (pos < 256) list[pos] = key; }
+            }
+            sync();
+            for (int i = tid; i < want && i < 256; i += 256) c[i] = list[i];
+            if (tid == 0) {
+                if (n_real >= jj) a.tau[q] = Pk;
+                a.cnt[q] = want < 256 ? want : 256;
+                if (lost) a.status[q] |= AVS_ST_OVERFLOW;
+            }
+        } else {
+            u64* tk = a.topkeys + (size_t)q * a.kprime;
+            for (int i = tid; i < n; i += 256) {
+                const u64 key = c[i];
+                if (key >= Pk && key != 0ull) { const int pos = atomicAdd(&misc[0], 1); if (pos < a.kprime) tk[pos] = key; }
+            }
+            for (int i = want + tid; i < a.kprime; i += 256) tk[i] = 0ull;
+            if (tid == 0) {
+                a.cnt[q] = dense_total > 0 ? n : total_in;             // dense level: slots (zero = empty), not keys
+                wsel_emit_final(a, q, n_real, Pk, lost);
+            }
+        }
+    }
+    sync();
 }

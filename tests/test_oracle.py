@@ -166,3 +166,22 @@ def test_shard_bounds():
     assert fs.shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert fs.shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     assert fs.shard_bounds(0, 2) == [(0, 0), (0, 0)]
+
+
+def test_dedup_pk_policy_cannot_change_the_reference_sized_answers(f1):
+    """The shipped database repeats primary keys (`/root/reference/milvus/RAG.py:507`: ids restart per speaker), and
+    whether Milvus Lite returns or collapses them cannot be pinned offline.  This bounds the consequence: at every limit
+    the reference uses (top-1 pipeline `milvus/search_json.py:411`, top-3 CLI default `milvus/search_embeddings.py:64`,
+    top-5) both policies give the SAME lists for all 130 self-queries and the 64 perturbed C1 queries; they first differ
+    at limit 10 (13 / 130), and with dedup a query can return at most 21 hits (the distinct keys)."""
+    X, pks, kat = f1["X"], f1["pks"], f1["kat"]
+    for Q in (X, kat["pert_queries"]):
+        for k in (1, 3, 5):
+            a = fs.search(X, pks, Q, k, "COSINE")
+            b = fs.search(X, pks, Q, k, "COSINE", dedup_pk=True)
+            assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0])
+    a = fs.search(X, pks, X, 10, "COSINE")
+    b = fs.search(X, pks, X, 10, "COSINE", dedup_pk=True)
+    assert sum(not np.array_equal(a[2][i], b[2][i]) for i in range(130)) == 13
+    b30 = fs.search(X, pks, X[:4], 30, "COSINE", dedup_pk=True)
+    assert np.unique(pks).size == 21 and np.all((b30[0] >= 0).sum(axis=1) == 21)
