@@ -39,7 +39,7 @@ constexpr int BLOCK_N = 256;        // database rows per tile (== AVS_GROUP_ROWS
 constexpr int BLOCK_K = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
-constexpr int TAU_CACHE = 1024;         // thresholds of the queries THIS CTA sweeps (128 per query block), cached in smem
+constexpr int TAU_CACHE = 2048;         // thresholds (as fp32 scores) of the queries THIS CTA sweeps (128 per query block), cached in smem
 constexpr int STASH = 4;                // per-thread survivor stash (keys) between slot reservations
 constexpr int RAW = 2;                  // per-thread raw stash: qualifying 8-score groups of the current tile, expanded after
                                         // the accumulator has been handed back to the MMA
@@ -56,7 +56,7 @@ template <int CG> struct Cfg {
     static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = CG == 1 ? 4 : 6;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAU_CACHE * 8 + 8 * WARP_STASH_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAU_CACHE * 4 + 8 * WARP_STASH_BYTES;
     static_assert(SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 };
 
@@ -224,8 +224,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* tfull_bar = bars + 2 * C::STAGES;      // [2] accumulator ready for the epilogue
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2; // [2] accumulator drained (leader CTA's copy is live)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-    u64* tau_smem = reinterpret_cast<u64*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    u64* stash_smem = tau_smem + TAU_CACHE;
+    float* tau_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    u64* stash_smem = reinterpret_cast<u64*>(tau_smem + TAU_CACHE);
     const int n_tau = n_qblocks * BLOCK_M;           // queries this CTA sweeps: 128 of every query block
     const bool tau_cached = n_tau <= TAU_CACHE;
     const u64* __restrict__ tau = plan.tau;
@@ -355,8 +355,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const AvsLevel& lv = plan.lv[l];
         const int64_t n_tiles = lv.n_visit * n_qblocks;
         if (tau_cached) {                              // this level's thresholds (the previous select wrote them)
-            for (int i = threadIdx.x - 128; i < n_tau; i += 256)
-                tau_smem[i] = tau[((i / BLOCK_M) * CG + (int)cta_rank) * BLOCK_M + (i % BLOCK_M)];
+            for (int i = threadIdx.x - 128; i < n_tau; i += 256) {
+                const u64 tk = tau[((i / BLOCK_M) * CG + (int)cta_rank) * BLOCK_M + (i % BLOCK_M)];
+                tau_smem[i] = tk == 0ull ? -INFINITY : avs_key_score(tk);   // NaN for padding slots (key ~0): never accepts
+            }
             epi_sync();
         }
         // the tile loop exists twice - threshold-free (dense) level and thresholded levels - so that the dense level's
@@ -370,8 +372,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const bool has_pad = row0 + 128 > n_rows;  // only the last group of the store can hold padding rows
             const int valid_cols = has_pad ? (int)(n_rows > row0 ? n_rows - row0 : 0) : 128;
             const int q = (qb * CG + (int)cta_rank) * BLOCK_M + ew * 32 + lane;
-            const u64 tau_k = tau_cached ? tau_smem[qb * BLOCK_M + ew * 32 + lane] : tau[q];
-            const float tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k);  // NaN for padding slots: never accepts
+            float tau_f;
+            if (tau_cached) tau_f = tau_smem[qb * BLOCK_M + ew * 32 + lane];
+            else { const u64 tau_k = tau[q]; tau_f = tau_k == 0ull ? -INFINITY : avs_key_score(tau_k); }   // NaN for padding slots
             u64* const my_cand = cand + (size_t)q * cap;
             flush_pending();
             int n_stash = 0, n_raw = 0;

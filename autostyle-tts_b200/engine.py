@@ -52,7 +52,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("AVS_LIB") or LIB_PATH      # AVS_LIB: A/B runs of an older build of the library (profiles/)
     if not os.path.exists(p):
         raise ImportError(
             f"{p} is missing: build it with `python autostyle-tts_b200/build.py` "
@@ -88,6 +88,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "avs_version": (ctypes.c_char_p, []),
     }
     for name, (res, args) in protos.items():
+        if os.environ.get("AVS_LIB") and not hasattr(lib, name):
+            continue                                       # an older build does not export the newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
