@@ -182,6 +182,7 @@ struct avs_store {
     void* nccl_comm = nullptr;
     void* p2p_state = nullptr;       // peer-memory exchange regions (comm.cu)
     int opt_p2p = 1;
+    long long opt_p2p_timeout_ms = 0;  // wall-clock bound of a wait for a peer in the exchange kernels (0: default, 120 s)
     int opt_final_sigma = 2;         // expected survivors of the last level = K' + sigma * sqrt(K' * ratio)
     int opt_fine_min_batch = 129;    // tensor-core path: batches from here on use the fine (x4) dense-end schedule
     int opt_coarse_sigma = 3;        // same margin for the coarse (x32) schedule of the tensor-core path (gemv: 8)

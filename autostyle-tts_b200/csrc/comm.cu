@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) shard_merge_kernel(const GatherItem* __re
 // Every CTA of every rank finishes phase 1 without waiting for anybody, hence every wait of phase 2 completes
 // whatever the dispatch order.  Two parities alternate between searches: a rank can only be one search ahead of
 // its slowest peer (it needs that peer's push to finish its own merge), so a region is never overwritten while it
-// is still being read.  A spin that gives up (a peer died) poisons the query's output (id -1, score -inf) and
+// is still being read.  A wait that gives up (wall-clock bound, a peer died) poisons the query's output (id -1, score -inf) and
 // bumps `timeouts`, which the host mirrors into pinned memory: the next call fails with AVS_E_NCCL.
 // ---------------------------------------------------------------------------------------------
 #define P2P_MAX_WORLD 8
@@ -123,7 +123,25 @@ __global__ void __launch_bounds__(256) shard_merge_kernel(const GatherItem* __re
 #define P2P_MAX_NQ (1 << 14)
 #define P2P_Q_FLOATS (1 << 23)               // query all-gather buffer per parity (32 MiB of fp32)
 #define P2P_Q_CTAS 128                       // CTAs of the query all-gather kernel (one completion flag each)
-#define P2P_SPIN_LIMIT (1ll << 27)
+#define P2P_TIMEOUT_MS_DEFAULT 120000        // wall-clock bound of a wait for a peer (option "p2p_timeout_ms")
+
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until *f shows seq.  The bound is WALL-CLOCK time (globaltimer), not a spin count: a peer that is merely late
+// (its host is busy between two searches) must not be mistaken for a dead one.  Returns false when the wait gave up.
+__device__ __forceinline__ bool p2p_wait_flag(volatile unsigned int* f, unsigned int seq, unsigned long long timeout_ns) {
+    if (*f == seq) return true;
+    const unsigned long long t0 = p2p_now_ns();
+    for (;;) {
+        for (int i = 0; i < 256; ++i)
+            if (*f == seq) return true;
+        if (p2p_now_ns() - t0 > timeout_ns) return false;
+        __nanosleep(200);
+    }
+}
 
 struct P2PRegion {                            // layout of one rank's exchange region
     GatherItem items[2][P2P_MAX_WORLD][P2P_ITEMS_PER_SRC];
@@ -147,7 +165,7 @@ struct P2PState {
 };
 
 __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers, int rank, int world, unsigned int seq,
-                                                                 int nq, int k, const double* __restrict__ s64,
+                                                                 unsigned long long timeout_ns, int nq, int k, const double* __restrict__ s64,
                                                                  int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
     extern __shared__ unsigned char raw[];
     GatherItem* sm = reinterpret_cast<GatherItem*>(raw);
@@ -170,18 +188,14 @@ __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers,
             *f = seq;
         }
     }
-    // phase 2: wait for every rank's items of my queries in MY region (bounded spin: a missing peer must not hang the GPU)
+    // phase 2: wait for every rank's items of my queries in MY region (wall-clock bounded wait: a missing peer must not hang the GPU)
     P2PRegion* mine = peers.r[rank];
     for (int q = blockIdx.x; q < nq; q += gridDim.x) {
         const size_t slot = (size_t)q * k;
         if (threadIdx.x == 0) s_dead = 0;
         __syncthreads();
         if (threadIdx.x < world) {
-            volatile unsigned int* f = &mine->flags[par][threadIdx.x][q];
-            long long spins = 0;
-            while (*f != seq) {
-                if (++spins > P2P_SPIN_LIMIT) { atomicAdd(&mine->timeouts, 1u); s_dead = 1; break; }
-            }
+            if (!p2p_wait_flag(&mine->flags[par][threadIdx.x][q], seq, timeout_ns)) { atomicAdd(&mine->timeouts, 1u); s_dead = 1; }
         }
         __syncthreads();
         __threadfence_system();
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(256) p2p_exchange_merge_kernel(P2PPeers peers,
 // and waits until every rank's slice has landed here.  The search that follows on the stream reads the whole batch
 // from the local region.
 __global__ void __launch_bounds__(256) p2p_query_allgather_kernel(P2PPeers peers, int rank, int world, unsigned int seq,
-                                                                  size_t lo4, size_t hi4 /* my slice, in float4 units */) {
+                                                                  unsigned long long timeout_ns, size_t lo4, size_t hi4 /* my slice, in float4 units */) {
     const int par = seq & 1;
     const float4* src = reinterpret_cast<const float4*>(peers.r[rank]->qbuf[par]);
     for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (size_t)gridDim.x * blockDim.x) {
@@ -250,11 +264,7 @@ __global__ void __launch_bounds__(256) p2p_query_allgather_kernel(P2PPeers peers
     P2PRegion* mine = peers.r[rank];
     // every CTA waits for a share of the (source rank, source CTA) flags; the kernel ends when all have been seen
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < world * (int)gridDim.x; i += gridDim.x * blockDim.x) {
-        volatile unsigned int* f = &mine->qflags[par][i / gridDim.x][i % gridDim.x];
-        long long spins = 0;
-        while (*f != seq) {
-            if (++spins > P2P_SPIN_LIMIT) { atomicAdd(&mine->timeouts, 1u); break; }
-        }
+        if (!p2p_wait_flag(&mine->qflags[par][i / gridDim.x][i % gridDim.x], seq, timeout_ns)) atomicAdd(&mine->timeouts, 1u);
     }
     __threadfence_system();
 }
@@ -272,7 +282,7 @@ static void p2p_free(avs_store* s) {
     s->p2p_state = nullptr;
 }
 
-// number of bounded spins that gave up waiting for a peer (0 in a healthy job); read by avs_get_stat("p2p_timeouts")
+// number of bounded waits that gave up waiting for a peer (0 in a healthy job); read by avs_get_stat("p2p_timeouts")
 int avs_p2p_timeouts(avs_store* s, int64_t* out) {
     P2PState* st = (P2PState*)s->p2p_state;
     *out = 0;
@@ -403,6 +413,11 @@ static int p2p_check_health(avs_store* s, P2PState* p2p) {
     return AVS_OK;
 }
 
+static unsigned long long p2p_timeout_ns(const avs_store* s) {
+    const long long ms = s->opt_p2p_timeout_ms > 0 ? s->opt_p2p_timeout_ms : P2P_TIMEOUT_MS_DEFAULT;
+    return (unsigned long long)ms * 1000000ull;
+}
+
 static int exchange_and_merge(avs_store* s, int nq, int k, int64_t* out_ids, float* out_scores, cudaStream_t st, bool use_p2p) {
     AvsScratch& c = s->sc;
     P2PState* p2p = (P2PState*)s->p2p_state;
@@ -421,7 +436,7 @@ static int exchange_and_merge(avs_store* s, int nq, int k, int64_t* out_ids, flo
             }
             AVS_CUDA(cudaEventRecord(p2p->tev[2 * p2p->tev_used], st));
         }
-        p2p_exchange_merge_kernel<<<grid, 256, (size_t)P * sizeof(GatherItem), st>>>(p2p->peers, s->rank, s->world, p2p->seq, nq, k,
+        p2p_exchange_merge_kernel<<<grid, 256, (size_t)P * sizeof(GatherItem), st>>>(p2p->peers, s->rank, s->world, p2p->seq, p2p_timeout_ns(s), nq, k,
                                                                                    c.out_s64, out_ids, out_scores);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());
@@ -512,7 +527,7 @@ extern "C" int avs_search_sharded_host(avs_store* s, const float* q_host, int nq
             if (!pinned) { memcpy(c.h_q + off, q_host + off, nb); src = c.h_q + off; }
             AVS_CUDA(cudaMemcpyAsync(qbuf + off, src, nb, cudaMemcpyHostToDevice, st));
         }
-        p2p_query_allgather_kernel<<<P2P_Q_CTAS, 256, 0, st>>>(p2p->peers, s->rank, s->world, p2p->qseq,
+        p2p_query_allgather_kernel<<<P2P_Q_CTAS, 256, 0, st>>>(p2p->peers, s->rank, s->world, p2p->qseq, p2p_timeout_ns(s),
                                                                (size_t)lo * s->dim / 4, (size_t)hi * s->dim / 4);
         s->st_launches++;
         AVS_CUDA(cudaGetLastError());

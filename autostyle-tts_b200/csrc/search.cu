@@ -1473,6 +1473,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "force_repair") s->opt_force_repair = (int)value;
     else if (k == "cta_group") s->opt_cta_group = value == 2 ? 2 : 1;
     else if (k == "p2p_merge") s->opt_p2p = value != 0;
+    else if (k == "p2p_timeout_ms") s->opt_p2p_timeout_ms = value < 0 ? 0 : (long long)value;
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;

@@ -544,6 +544,7 @@ def measure(a, env, cfg):
         if rank == 0:
             parity = {"parity_ids_match_oracle": bool(rc["ids_match"] and rc["sound"]), **rc,
                       "what": f"hits of the timed batch-{main_b} call itself, {int(slots.size)} of its queries"}
+    barrier()       # rank 0 alone ran the oracle above: nobody enters the next collective search until it is back
     # batch-1 hits of the timed call: the single query is slot 0 of the batch
     if 1 in last_hits and main_b != 1:
         b1_ids = last_hits[1][0].cpu().numpy()
