@@ -19,6 +19,9 @@ typedef unsigned long long u64;
 #define AVS_MAX_LEVELS 12
 #define AVS_DENSE_CAP 65536      // rows of the threshold-free level of the gemv path (dense key buffer per query)
 #define AVS_DENSE_MAX_NQ 64      // the dense buffer is kept for this many queries
+#define AVS_TRACE_SEL (64 + AVS_MAX_LEVELS * 256 * 9)   // trace buffer: 16 phase stamps of CTA 0's level select per level start here
+#define AVS_TRACE_SLOTS (AVS_TRACE_SEL + AVS_MAX_LEVELS * 16)
+#define AVS_BOOT_J 8             // tensor-core path, boot level: keys kept per (row group half, query); the level's rank must not exceed it
 
 // ---- error plumbing -------------------------------------------------------------------------
 void avs_set_error(const char* fmt, ...);
@@ -77,6 +80,8 @@ struct AvsLevel {
     int64_t ratio;    // skip / stride (0 or 1: nothing skipped)
     int64_t n_visit;  // groups actually visited = n_iter - ceil(n_iter / ratio)
     int dense;   // 1: threshold-free level - every visited row is stored at slot (j*256 + column), no atomics
+                 // 2: threshold-free boot level of the tensor-core scan - only the AVS_BOOT_J best keys of every half
+                 //    group are stored (slot (j*2 + half)*AVS_BOOT_J + i): exact for any rank <= AVS_BOOT_J
 };
 
 // m-th row group a level visits: groups j*stride, j = 0.., leaving out every ratio-th j (seen by a sparser level)
@@ -171,7 +176,7 @@ struct avs_store {
         opt_cta_group = 2;
     // stats
     int64_t st_launches = 0, st_searches = 0, st_queries = 0, st_last_final_rows = 0;
-    int st_last_kprime = 0, st_last_levels = 0, st_last_path = 0;
+    int st_last_kprime = 0, st_last_levels = 0, st_last_path = 0, st_last_boot = 0;
     // scan timing hook
     bool timing = false;
     std::vector<cudaEvent_t> tev;   // event pairs around the dominant scan launches
@@ -188,6 +193,7 @@ struct avs_store {
     int opt_coarse_sigma = 3;        // same margin for the coarse (x32) schedule of the tensor-core path (gemv: 8)
     int opt_cta_group_small = 1;     // CTA-group size for batches of at most 128 queries (1: M = 128, half the MMA work)
     int opt_dense_rows = AVS_DENSE_CAP;   // rows of the gemv path's threshold-free level (<= AVS_DENSE_CAP)
+    int opt_boot = 1;                // tensor-core path: threshold-free level as per-thread top-J lists (AvsLevel::dense == 2)
     int opt_hybrid = 1;              // auto mode, <= 8 queries: gemv dense level, tensor-core scan for the later levels
     int opt_gemm_dense_rows = 2048;  // rows of the tensor-core path's threshold-free level (inside the candidate buffer)
     int opt_finalize_threads = 0;    // 0: 1024 threads per query up to 64 queries, 256 beyond

@@ -149,6 +149,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PipeState {
@@ -363,8 +370,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         // the tile loop exists twice - threshold-free (dense) level and thresholded levels - so that the dense level's
         // store code does not sit inside the hot loop of the thresholded levels
-        auto run_tiles = [&](auto dense_tag) {
-        constexpr bool DENSE = decltype(dense_tag)::value;
+        auto run_tiles = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;      // 0 thresholded, 1 dense (every key stored), 2 boot (top-J per thread)
+        constexpr bool DENSE = MODE == 1;
+        constexpr bool BOOT = MODE == 2;
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
             const int64_t m = t / n_qblocks;
             const int qb = (int)(t - m * n_qblocks);
@@ -378,6 +387,13 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             u64* const my_cand = cand + (size_t)q * cap;
             flush_pending();
             int n_stash = 0, n_raw = 0;
+            // boot level: this thread's BOOT_J best scores of the tile half (sorted, score desc then column asc) and their columns
+            float bs[BOOT ? AVS_BOOT_J : 1];
+            int bc[BOOT ? AVS_BOOT_J : 1];
+            if constexpr (BOOT) {
+#pragma unroll
+                for (int i = 0; i < AVS_BOOT_J; ++i) { bs[i] = -INFINITY; bc[i] = -1; }
+            }
             auto reserve = [&]() {
                 pend_n = n_stash;
                 pend_dst = my_cand;
@@ -466,6 +482,60 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N + half * 128;
+            if constexpr (BOOT) {
+                // Threshold-free level without a dense store: the rank-j key (j <= BOOT_J) of everything the level visits
+                // is the rank-j key of the union of the per-thread top-J lists, and every row at or above it is in one of
+                // them.  Sorted insertion, strict compare: equal scores keep column order (smaller row first = larger
+                // key).  Lanes without a real query skip the work (batch 1: one lane of two warps).  A rolled loop over
+                // 8-column slices keeps the code small (the level is a few tiles per CTA; its speed is not the issue).
+                const bool live = q < plan.nq;
+#pragma unroll 1
+                for (int c8 = 0; c8 < 128; c8 += 8) {
+                    uint32_t v8[8];
+                    __syncwarp();
+                    tmem_ld8(t_base + c8, v8);
+                    tmem_ld_wait();
+                    if (live) {
+                        uint32_t allow = 0xFFu;
+                        if (filt) allow = (filt[(row0 + c8) >> 5] >> (c8 & 31)) & 0xFFu;
+                        const int vc = valid_cols - c8;
+                        allow = vc >= 8 ? allow : (vc <= 0 ? 0u : (allow & ((1u << vc) - 1)));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float sc = __uint_as_float(v8[i]);
+                            if (sc > bs[AVS_BOOT_J - 1] && ((allow >> i) & 1u)) {
+#pragma unroll
+                                for (int p = AVS_BOOT_J - 1; p > 0; --p) {
+                                    const bool up = sc > bs[p - 1];
+                                    const bool here = !up && sc > bs[p];
+                                    bs[p] = up ? bs[p - 1] : (here ? sc : bs[p]);
+                                    bc[p] = up ? bc[p - 1] : (here ? c8 + i : bc[p]);
+                                }
+                                if (sc > bs[0]) { bs[0] = sc; bc[0] = c8 + i; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
+                    else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
+                }
+                // slot block (group ordinal m, tile half) of the query's buffer: BOOT_J keys, 0 = empty
+                if (live) {
+                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(my_cand + ((size_t)m * 2 + half) * AVS_BOOT_J);
+#pragma unroll
+                    for (int i = 0; i < AVS_BOOT_J; i += 2) {
+                        ulonglong2 kk;
+                        kk.x = bc[i] >= 0 ? avs_make_key(bs[i], (uint32_t)(row0 + bc[i])) : 0ull;
+                        kk.y = bc[i + 1] >= 0 ? avs_make_key(bs[i + 1], (uint32_t)(row0 + bc[i + 1])) : 0ull;
+                        dst[i >> 1] = kk;
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             uint32_t va[32], vb[32];
             __syncwarp();
             tmem_ld32(t_base, va);
@@ -495,7 +565,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         };
-        if (lv.dense) run_tiles(std::true_type{}); else run_tiles(std::false_type{});
+        if (lv.dense == 2) run_tiles(std::integral_constant<int, 2>{});
+        else if (lv.dense == 1) run_tiles(std::integral_constant<int, 1>{});
+        else run_tiles(std::integral_constant<int, 0>{});
         flush_pending();
         stamp(1 + 4 * l);                              // this CTA's tiles of the level are done
         if (plan.trace != nullptr && threadIdx.x == 128 && blockIdx.x < 256) {   // per-CTA finish time of the level (load balance)
@@ -508,11 +580,15 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         {
             const bool final_level = plan.last_is_final && l == plan.n_levels - 1;
             u64* const list = reinterpret_cast<u64*>(warp_stash);             // 2 KB of the (now idle) survivor stash of this warp
-            const int dense_total = lv.dense ? (int)(lv.n_visit * AVS_GROUP_ROWS) : 0;
+            const int dense_total = lv.dense == 2 ? (int)(lv.n_visit * 2 * AVS_BOOT_J) : lv.dense ? (int)(lv.n_visit * AVS_GROUP_ROWS) : 0;
             if (plan.nq <= (int)gridDim.x) {           // at most one query per CTA: its 8 epilogue warps share the select
-                if ((int)blockIdx.x < plan.nq)
-                    cta_select_level(plan, (int)blockIdx.x, warp - 4, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l],
-                                     stash_smem, []() { epi_sync(); });
+                if ((int)blockIdx.x < plan.nq) {
+                    u64* const tr = (plan.trace != nullptr && blockIdx.x == 0) ? plan.trace + AVS_TRACE_SEL + l * 16 : nullptr;
+                    if (!cta_select_fast(plan, (int)blockIdx.x, (int)threadIdx.x - 128, plan.j_rank[l], final_level, dense_total,
+                                         plan.k_eps[l], stash_smem, []() { epi_sync(); }, tr))
+                        cta_select_level(plan, (int)blockIdx.x, warp - 4, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l],
+                                         stash_smem, []() { epi_sync(); });
+                }
             } else {
                 for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
                     warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);

@@ -1120,8 +1120,8 @@ int avs_scratch_reserve(avs_store* s, int nq_pad, int kprime, int cap, int k) {
         AVS_CHECK(dev_alloc(&c.dense_buf, (size_t)(AVS_DENSE_MAX_NQ + 8) * AVS_DENSE_CAP));
         AVS_CHECK(dev_alloc(&c.rep_hist, (size_t)8 * 4096));
         AVS_CHECK(dev_alloc(&c.gbar, (size_t)4));
-        AVS_CHECK(dev_alloc(&c.trace, (size_t)64 + AVS_MAX_LEVELS * 256 * 9));
-        AVS_CUDA(cudaMemset(c.trace, 0, (64 + AVS_MAX_LEVELS * 256 * 9) * sizeof(u64)));
+        AVS_CHECK(dev_alloc(&c.trace, (size_t)AVS_TRACE_SLOTS));
+        AVS_CUDA(cudaMemset(c.trace, 0, AVS_TRACE_SLOTS * sizeof(u64)));
         AVS_CUDA(cudaMemset(c.gbar, 0, 4 * sizeof(unsigned int)));
     }
     c.nq_cap = nq2; c.kprime_cap = kp2; c.cap_cap = cap2; c.k_cap = k2;
@@ -1210,61 +1210,34 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // the warp-dot kernel and loses 5 % at D = 3072; for 3-8 queries the level saved (~35 us) pays off while the final
     // scan is short (C2: +10 %, 125 K-row shard: +37 %) but not on 20 GB shards, where the plain tensor-core schedule stays.
     const size_t scan_bytes = (size_t)s->count * s->dpad * 2;
-    const bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 &&
-                        ((nq <= 2 && s->dpad <= 1024) || (nq >= 3 && nq <= 8 && scan_bytes <= ((size_t)8 << 30)));
+    bool hybrid = s->opt_scan_path == 0 && s->opt_hybrid != 0 &&
+                  ((nq <= 2 && s->dpad <= 1024) || (nq >= 3 && nq <= 8 && scan_bytes <= ((size_t)8 << 30)));
     // auto mode without the hybrid pipeline: tensor-core scan from `gemm_min_batch` queries on, except 1-2 queries of
     // D > 1024, where the warp-dot kernel streams 5 % faster
-    const bool use_gemm = !hybrid && ((s->opt_scan_path == 2) ||
-                                      (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch && !(nq <= 2 && s->dpad > 1024)));
+    const bool gemm_eligible = (s->opt_scan_path == 2) ||
+                               (s->opt_scan_path == 0 && nq >= s->opt_gemm_min_batch && !(nq <= 2 && s->dpad > 1024));
+    bool use_gemm = !hybrid && gemm_eligible;
+    const bool hybrid_legacy = hybrid, use_gemm_legacy = use_gemm;
     // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th
     // row group not visited by a sparser level; the sparsest level must fit the collection buffer with
     // threshold 0.  The tensor-core path ends with a x4 step (its epilogue pays per accepted row, so the
     // last threshold is taken from a quarter of the database); the gemv path keeps fewer, coarser levels.
-    const bool fine_levels = use_gemm && nq >= s->opt_fine_min_batch;   // compute-bound regime only: extra levels cost launches
+    bool fine_levels = use_gemm && nq >= s->opt_fine_min_batch;   // compute-bound regime only: extra levels cost launches
     const int64_t G = (s->count + AVS_GROUP_ROWS - 1) / AVS_GROUP_ROWS;
     const int64_t rho = s->opt_ratio < 2 ? 2 : s->opt_ratio;
     int64_t strides[AVS_MAX_LEVELS];
-    int L = 1;
-    strides[0] = 1;
-    // the threshold-free level: <= 2048 rows inside the candidate buffer on the tensor-core path; the gemv path (few
-    // queries) stores up to 64 K rows densely in its own buffer, which saves it a whole intermediate level
-    const bool dense_gemv = !use_gemm && nq <= AVS_DENSE_MAX_NQ;
-    const int64_t level0_rows = dense_gemv ? s->opt_dense_rows : (cap < s->opt_gemm_dense_rows ? cap : s->opt_gemm_dense_rows);
-    while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
-        // tensor-core path: three x4 steps next to the dense end (its epilogue pays per accepted row, so the
-        // thresholds are refreshed often and kept tight), coarse steps for the sparse levels
-        int64_t r = (fine_levels && L <= 3) ? s->opt_fine_ratio : rho;
-        if (r == rho) {   // last coarse step: no sparser than needed to bring the threshold-free level under its row cap
-            const int64_t g_prev = (G + strides[L - 1] - 1) / strides[L - 1];
-            const int64_t r_needed = (g_prev * AVS_GROUP_ROWS + level0_rows - 1) / level0_rows;
-            if (r_needed < r) r = r_needed < 2 ? 2 : r_needed;
-        }
-        strides[L] = strides[L - 1] * r;
-        ++L;
-    }
     AvsLevel lv[AVS_MAX_LEVELS];
     int j_ranks[AVS_MAX_LEVELS];
-    for (int i = 0; i < L; ++i) {            // level 0 = sparsest
-        const int64_t stride = strides[L - 1 - i];
-        lv[i].stride = stride;
-        lv[i].n_iter = (G + stride - 1) / stride;
-        lv[i].skip = i == 0 ? 0 : strides[L - i];
-        lv[i].ratio = i == 0 ? 0 : lv[i].skip / stride;
-        lv[i].n_visit = lv[i].ratio > 1 ? lv[i].n_iter - (lv[i].n_iter + lv[i].ratio - 1) / lv[i].ratio : lv[i].n_iter;
-        lv[i].dense = (i == 0 && ((use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ||
-                                  (dense_gemv && lv[i].n_iter * AVS_GROUP_ROWS <= AVS_DENSE_CAP))) ? 1 : 0;
-        j_ranks[i] = 0;
-    }
-
+    int L = 1;
     // Threshold ranks, from the last level backwards.  The rank-j key of what level i has collected becomes the
     // threshold of level i+1, which then ends with about j*ratio survivors (relative spread ~ 1/sqrt(j)).  The
-    // last threshold must leave at least K' rows with a wide margin: K' + 8*sqrt(K'*ratio) expected survivors
-    // (K'=32, x4: 128; K'=256, x4: 512); every earlier level must hold comfortably more keys than the rank the
-    // next select asks for.
-    {
+    // last threshold must leave at least K' rows with a wide margin: K' + sigma*sqrt(K'*ratio) expected survivors;
+    // every earlier level must hold comfortably more keys than the rank the next select asks for.
+    auto set_ranks = [&]() {
         double need = 0.0;
+        for (int i = 0; i < L; ++i) j_ranks[i] = 0;
         for (int i = L - 2; i >= 0; --i) {
-            const double ratio = (double)(lv[i].stride / lv[i + 1].stride);
+            const double ratio = (double)(strides[L - 1 - i] / strides[L - 2 - i]);
             if (i == L - 2) need = (double)kprime + (double)(fine_levels ? s->opt_final_sigma : ((use_gemm || hybrid) ? s->opt_coarse_sigma : 8)) * sqrt((double)kprime * ratio);
             int64_t j = (int64_t)(need / ratio) + 1;
             if (j < 8) j = 8;
@@ -1272,11 +1245,86 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             j_ranks[i] = (int)j;
             need = 1.5 * (double)j + 16.0;
         }
+    };
+    // Sampling levels, built from the final (dense) level backwards: level l visits every stride_l-th row group not
+    // visited by a sparser level.  `level0_rows`: what the threshold-free level may visit.  `fine_steps`: how many x4
+    // steps sit next to the dense end on the compute-bound tensor-core schedule (its epilogue pays per accepted row,
+    // so the thresholds there are refreshed often and kept tight); coarse steps for the sparser levels.
+    auto build_strides = [&](int64_t level0_rows, int fine_steps, int64_t rho) {
+        L = 1;
+        strides[0] = 1;
+        while (((G + strides[L - 1] - 1) / strides[L - 1]) * AVS_GROUP_ROWS > level0_rows && L < AVS_MAX_LEVELS) {
+            int64_t r = (fine_levels && L <= fine_steps) ? s->opt_fine_ratio : rho;
+            if (r == rho) {   // last coarse step: no sparser than needed to bring the threshold-free level under its row cap
+                const int64_t g_prev = (G + strides[L - 1] - 1) / strides[L - 1];
+                const int64_t r_needed = (g_prev * AVS_GROUP_ROWS + level0_rows - 1) / level0_rows;
+                if (r_needed < r) r = r_needed < 2 ? 2 : r_needed;
+            }
+            strides[L] = strides[L - 1] * r;
+            ++L;
+        }
+    };
+    // Boot level (tensor-core path): the threshold-free level keeps only the AVS_BOOT_J best keys of every half group, so
+    // it may visit cap / (2 J) whole groups (32 K rows at K' = 32) instead of the 2 048 rows a dense store has room for -
+    // one or two levels fewer, and no warp-dot kernel + select launch in front of the scan for small batches.  Its rank
+    // must not exceed J: the sparsest ratio is raised until it does not; stores too small for that keep the dense level.
+    bool boot = false;
+    // (a store the warp-dot path searches in ONE dense level keeps that path: nothing to save there)
+    // boot = 1 (default): HBM-bound batches only (coarse schedule) - the boot epilogue (sorted insertion of 128 scores per
+    // thread and tile, ~15 us with every lane live) hides behind the 8.5 us a tile takes to stream only when few lanes
+    // are live or few tiles are scanned; measured at batch 1024 it cost 45 us more than the dense 2 048-row level.  boot = 2: always.
+    const bool boot_wanted = s->opt_boot == 2 || (s->opt_boot == 1 && nq < s->opt_fine_min_batch);
+    if (boot_wanted && gemm_eligible && !(hybrid_legacy && s->count <= (int64_t)s->opt_dense_rows)) {
+        use_gemm = true; hybrid = false;              // with a boot level the tensor-core scan takes every level, small batches too
+        fine_levels = nq >= s->opt_fine_min_batch;
+        const int64_t boot_groups = cap / (2 * AVS_BOOT_J);
+        // HBM-bound batches: a level costs two grid barriers and a select, an accepted row next to nothing - allow a
+        // sparser boot level (up to cap / 32: 8 * ratio expected survivors fill a quarter of the buffer at most)
+        int64_t rho_boot = rho;
+        if (!fine_levels) { const int64_t m = cap / 32 < 128 ? cap / 32 : 128; rho_boot = rho > m ? rho : m; }
+        build_strides(boot_groups * AVS_GROUP_ROWS, 1, rho_boot);
+        // the whole store inside the boot budget, but too large for ONE dense level: a boot level in front of the final one
+        if (L == 1 && G * AVS_GROUP_ROWS > (cap < s->opt_gemm_dense_rows ? cap : s->opt_gemm_dense_rows)) {
+            strides[1] = fine_levels ? s->opt_fine_ratio : 2;
+            L = 2;
+        }
+        if (L >= 2 && !(fine_levels && L == 2 && s->eps_rule)) {   // the eps rule asks the last select for rank k > J
+            for (int it = 0; it < 64; ++it) {
+                set_ranks();
+                if (j_ranks[0] <= AVS_BOOT_J) break;
+                const int64_t r = strides[L - 1] / strides[L - 2];
+                strides[L - 1] = strides[L - 2] * (r + (r + 3) / 4);
+            }
+            const int64_t ratio0 = strides[L - 1] / strides[L - 2];
+            const int64_t g0 = (G + strides[L - 1] - 1) / strides[L - 1];
+            boot = j_ranks[0] <= AVS_BOOT_J && g0 >= 1 && g0 <= boot_groups && (int64_t)j_ranks[0] * ratio0 * 4 <= cap;
+        }
+    }
+    if (!boot) { use_gemm = use_gemm_legacy; hybrid = hybrid_legacy; fine_levels = use_gemm && nq >= s->opt_fine_min_batch; }
+    const bool dense_gemv = !use_gemm && nq <= AVS_DENSE_MAX_NQ;
+    if (!boot) {
+        // the threshold-free level: <= 2048 rows inside the candidate buffer on the tensor-core path; the gemv path (few
+        // queries) stores up to 64 K rows densely in its own buffer, which saves it a whole intermediate level
+        const int64_t level0_rows = dense_gemv ? s->opt_dense_rows : (cap < s->opt_gemm_dense_rows ? cap : s->opt_gemm_dense_rows);
+        build_strides(level0_rows, 3, rho);
+        set_ranks();
+    }
+    for (int i = 0; i < L; ++i) {            // level 0 = sparsest
+        const int64_t stride = strides[L - 1 - i];
+        lv[i].stride = stride;
+        lv[i].n_iter = (G + stride - 1) / stride;
+        lv[i].skip = i == 0 ? 0 : strides[L - i];
+        lv[i].ratio = i == 0 ? 0 : lv[i].skip / stride;
+        lv[i].n_visit = lv[i].ratio > 1 ? lv[i].n_iter - (lv[i].n_iter + lv[i].ratio - 1) / lv[i].ratio : lv[i].n_iter;
+        lv[i].dense = (i == 0 && boot) ? 2 :
+                      (i == 0 && ((use_gemm && lv[i].n_iter * AVS_GROUP_ROWS <= cap) ||
+                                  (dense_gemv && lv[i].n_iter * AVS_GROUP_ROWS <= AVS_DENSE_CAP))) ? 1 : 0;
     }
 
     s->st_last_final_rows = L > 1 ? (G - (G + strides[1] - 1) / strides[1]) * AVS_GROUP_ROWS : s->count;   // warp-dot path: its final level
     s->st_last_kprime = kprime;
     s->st_last_levels = L;
+    s->st_last_boot = boot ? 1 : 0;
     const bool hybrid_on = hybrid && L > 1 && lv[0].dense;   // single-level searches stay on the gemv kernels
     const bool any_gemm = use_gemm || hybrid_on;
     const float* eps_used = any_gemm ? c.eps_gemm : c.eps_gemv;   // prep makes eps_gemm >= eps_gemv
@@ -1477,6 +1525,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
+    else if (k == "boot") s->opt_boot = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));
@@ -1496,13 +1545,14 @@ extern "C" int avs_get_stat(avs_store* s, const char* key, int64_t* out) {
     else if (k == "queries") *out = s->st_queries;
     else if (k == "last_kprime") *out = s->st_last_kprime;
     else if (k == "last_levels") *out = s->st_last_levels;
+    else if (k == "last_boot") *out = s->st_last_boot;
     else if (k == "last_final_rows") *out = s->st_last_final_rows;
     else if (k == "p2p_timeouts") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_timeouts(s, out); }
     else if (k == "exchange_us") { AVS_CUDA(cudaSetDevice(s->device)); return avs_p2p_exchange_us(s, out); }
     else if (k == "last_scan_path") *out = s->st_last_path;
     else if (k.rfind("trace:", 0) == 0) {      // phase timestamp i (ns, globaltimer) of the last persistent scan: synchronises
         const int i = atoi(k.c_str() + 6);
-        if (i < 0 || i >= 64 + AVS_MAX_LEVELS * 256 * 9 || !s->sc.trace) { avs_set_error("avs_get_stat: trace slot out of range"); return AVS_E_INVALID; }
+        if (i < 0 || i >= AVS_TRACE_SLOTS || !s->sc.trace) { avs_set_error("avs_get_stat: trace slot out of range"); return AVS_E_INVALID; }
         AVS_CUDA(cudaSetDevice(s->device));
         u64 v = 0;
         AVS_CUDA(cudaMemcpy(&v, s->sc.trace + i, sizeof(v), cudaMemcpyDeviceToHost));

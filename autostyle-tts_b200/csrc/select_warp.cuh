@@ -185,7 +185,7 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
     // compacted into the warp's list and then take the register-sort path below
     const u64* src = c;
     int n_src = n;
-    if (n > 256 && dense_total > 0 && !is_final && jj <= 32) {
+    if (n > 256 && dense_total > 0 && !is_final && jj <= 32 && k_eps == 0) {   // eps rule: the threshold may end up below the pivot
         u64 lm = 0;
 #pragma unroll 8
         for (int i = lane; i < n; i += 32) { const u64 key = c[i]; lm = key > lm ? key : lm; }   // 8 loads in flight per lane
@@ -311,6 +311,141 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lean CTA select for the common small-batch cases (one query per CTA, 256 threads): a chain of as few dependent steps
+// as possible, because the whole grid waits for it.
+//   threshold-free level (dense or boot lists, <= 2048 slots, rank <= 32): every thread loads 8 slots at once and
+//       publishes their maximum; the rank-j maximum (counted against the 256 maxima in shared memory, broadcast reads)
+//       is a lower bound of the rank-j key; the few keys at or above it are compacted into shared memory;
+//   <= 512 keys: every thread ranks its (at most two) keys by counting against all keys in shared memory; writing
+//       key -> slot[rank] leaves them sorted.
+// Same outputs as cta_select_level.  Returns false (uniformly, before writing anything) when the case is not covered.
+//   `scratch`: >= 1300 u64 of shared memory; `tr`: optional phase stamps (profiling).
+// ---------------------------------------------------------------------------------------------
+template <typename SyncFn>
+__device__ __noinline__ bool cta_select_fast(const WarpSelectArgs& a, int q, int tid, int j_rank, bool is_final,
+                                             int dense_total, int k_eps, u64* scratch, SyncFn sync, u64* tr) {
+    u64* const maxima = scratch;                                     // [256]
+    u64* const list = scratch + 256;                                 // [1024]
+    u64* const pub = scratch + 1280;                                 // [0] rank-(j-1) key, [1] rank-(k_eps-1) key, [2] K'-th key, [3] pivot
+    int* const misc = reinterpret_cast<int*>(scratch + 1284);        // [0] list fill, [1] real keys, [2] keys >= eps threshold
+    auto stamp = [&](int i) {
+        if (tr != nullptr && tid == 0) { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[i] = t; }
+    };
+    stamp(0);
+    u64* c = a.cand + (size_t)q * a.cap;
+    const int total_in = dense_total > 0 ? dense_total : a.cnt[q];
+    if (dense_total == 0 && total_in > a.cap) return false;          // keys were lost: the general path scales the rank
+    const int n = total_in;
+    // (under the eps rule the threshold may end up BELOW the pivot, whose compaction would already have dropped rows)
+    const bool pivot_case = dense_total > 0 && !is_final && j_rank <= 32 && n > 512 && n <= 2048 && k_eps == 0;
+    if (!pivot_case && n > 512) return false;
+    const int lane = tid & 31;
+    if (tid < 4) { pub[tid] = 0ull; misc[tid] = 0; }
+    int n_src = n;
+    if (pivot_case) {
+        u64 mine[8];
+        u64 lm = 0;
+        {
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(c + 8 * tid);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                if (8 * tid + 2 * r < n) v = p[r];                   // n is a multiple of 8 for both kinds of level
+                mine[2 * r] = v.x; mine[2 * r + 1] = v.y;
+                lm = v.x > lm ? v.x : lm;
+                lm = v.y > lm ? v.y : lm;
+            }
+        }
+        maxima[tid] = lm;
+        sync();
+        stamp(1);
+        int rk = 0;
+#pragma unroll 8
+        for (int i = 0; i < 256; ++i) rk += maxima[i] > lm ? 1 : 0;
+        if (lm != 0ull && rk == j_rank - 1) pub[3] = lm;             // keys are distinct: at most one thread
+        sync();
+        stamp(2);
+        const u64 P = pub[3];
+        if (P == 0ull) return false;                                 // fewer than j real maxima (row filter): general path
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (mine[r] >= P) { const int pos = atomicAdd(&misc[0], 1); list[pos] = mine[r]; }   // <= 8 j <= 256 keys
+        sync();
+        stamp(3);
+        n_src = misc[0];
+    } else {
+        for (int i = tid; i < n; i += 256) list[i] = c[i];
+        sync();
+        stamp(3);
+    }
+    // ---- rank every key by counting (n_src <= 512: two keys per thread) ----
+    const u64 k0 = tid < n_src ? list[tid] : 0ull, k1 = tid + 256 < n_src ? list[tid + 256] : 0ull;
+    int r0 = 0, r1 = 0;
+    if (n_src <= 256) {
+#pragma unroll 8
+        for (int i = 0; i < n_src; ++i) r0 += list[i] > k0 ? 1 : 0;
+    } else {
+#pragma unroll 8
+        for (int i = 0; i < n_src; ++i) { const u64 b = list[i]; r0 += b > k0 ? 1 : 0; r1 += b > k1 ? 1 : 0; }
+    }
+    {
+        int real = (k0 != 0ull) + (k1 != 0ull);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) real += __shfl_xor_sync(0xffffffffu, real, o);
+        if (lane == 0 && real) atomicAdd(&misc[1], real);
+    }
+    const int jj = j_rank;
+    if (!is_final) {
+        if (k0 != 0ull && r0 == jj - 1) pub[0] = k0;
+        if (k1 != 0ull && r1 == jj - 1) pub[0] = k1;
+        if (k_eps > 0) {
+            if (k0 != 0ull && r0 == k_eps - 1) pub[1] = k0;
+            if (k1 != 0ull && r1 == k_eps - 1) pub[1] = k1;
+        }
+    } else {
+        if (k0 != 0ull && r0 == a.kprime - 1) pub[2] = k0;
+        if (k1 != 0ull && r1 == a.kprime - 1) pub[2] = k1;
+    }
+    sync();                                                          // ranks done: `list` has been read by everybody
+    stamp(4);
+    const int n_real = misc[1];
+    if (!is_final) {
+        int keep = n_real >= jj ? jj : n_real;
+        u64 tau_new = n_real >= jj ? pub[0] : a.tau[q];
+        bool lowered = false;
+        // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
+        if (k_eps > 0 && n_real >= k_eps) {
+            const u64 t_eps = avs_make_key(avs_key_score(pub[1]) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            if (t_eps < tau_new) { tau_new = t_eps; lowered = true; }
+        }
+        if (lowered) {                                               // uniform: every thread read the same shared values
+            int above = (k0 != 0ull && k0 >= tau_new) + (k1 != 0ull && k1 >= tau_new);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+            if (lane == 0 && above) atomicAdd(&misc[2], above);
+            sync();
+            keep = misc[2];
+        }
+        if (k0 != 0ull && r0 < keep) c[r0] = k0;
+        if (k1 != 0ull && r1 < keep) c[r1] = k1;
+        if (tid == 0) { a.tau[q] = tau_new; a.cnt[q] = keep; }
+    } else {
+        const int m = n_real < a.kprime ? n_real : a.kprime;
+        u64* tk = a.topkeys + (size_t)q * a.kprime;
+        if (k0 != 0ull) { if (r0 < m) tk[r0] = k0; c[r0] = k0; }    // sorted and compacted: the wide-rescoring stage reads it
+        if (k1 != 0ull) { if (r1 < m) tk[r1] = k1; c[r1] = k1; }
+        for (int i = m + tid; i < a.kprime; i += 256) tk[i] = 0ull;
+        if (tid == 0) {
+            a.cnt[q] = dense_total > 0 ? n_real : total_in;           // dense level: compacted, no empty slots left in front
+            wsel_emit_final(a, q, n_real, n_real >= a.kprime ? pub[2] : 0ull, false);
+        }
+    }
+    sync();
+    stamp(5);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Few queries (at most one per CTA - the reference's batch-1 search): the 8 epilogue warps of a CTA select for ONE query
 // together instead of leaving it to a lone warp whose latency the whole grid waits for.  Same results as
 // warp_select_level; the rank counting (the n^2 part) and the dense level's slot scan are split 8 ways.
@@ -339,7 +474,7 @@ __device__ __noinline__ void cta_select_level(const WarpSelectArgs& a, int q, in
     sync();
 
     // ---- dense level, small rank: pivot = rank-j value of the 256 lane maxima, each warp scanning an eighth of the slots ----
-    if (n > 256 && n <= 2048 && dense_total > 0 && !is_final && jj <= 32) {
+    if (n > 256 && n <= 2048 && dense_total > 0 && !is_final && jj <= 32 && k_eps == 0) {
         u64 mine[8];
         u64 lm = 0;
         const int per = (n + 7) >> 3, lo = w * per, hi = lo + per < n ? lo + per : n;

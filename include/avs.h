@@ -133,7 +133,12 @@ int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out);
 int avs_p2p_connect(avs_store* s, const void* handles, int world);
 
 /* Options: "scan_path" 0=auto 1=gemv 2=gemm; "hybrid" 0|1 (auto mode, <= 8 queries: dense warp-dot level, tensor-core
- * scan for the later levels; default 1); "oversample" K' override (0=auto); "gemm_min_batch";
+ * scan for the later levels; default 1 - only used where the boot level below does not apply); "boot" 0|1|2 (tensor-core
+ * scan: the threshold-free level keeps the 8 best keys of every half row group instead of storing every key, so it
+ * may visit up to 32 K rows and every level runs in the ONE persistent launch; 1 = for HBM-bound batches (fewer than
+ * "fine_min_batch" queries; default), 2 = always, 0 = never);
+ * "p2p_timeout_ms" (wall-clock bound of a wait for a peer in the exchange kernels, default 120000);
+ * "oversample" K' override (0=auto); "gemm_min_batch";
  * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant) and "cta_group_small" 1|2 (the variant for batches of at most
  * 128 queries; default 1: M = 128 queries per CTA, half the padded MMA work); schedule knobs "fine_ratio",
  * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "force_repair" (testing: 1 = force the
@@ -142,7 +147,7 @@ int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
  * "uncertified_queries", "p2p_timeouts", "exchange_us" (mean duration of the peer-memory exchange kernel while
- * avs_scan_timing is on), "last_kprime", "last_levels", "last_scan_path", "last_final_rows";
+ * avs_scan_timing is on), "last_kprime", "last_levels", "last_boot", "last_scan_path", "last_final_rows";
  * "barrier_timeouts" (a grid barrier of a persistent kernel gave up: must stay 0);
  * "last_uncertified": queries of the last avs_search_host call whose top-k could not be proven exact - read without a
  * device synchronisation.  Every query whose certificate fails is settled by the exact float64 repair (all of them, in

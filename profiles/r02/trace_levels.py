@@ -75,6 +75,11 @@ def main():
                             acc.append({"cta": cta, "warp": 4 if w == 0 else 11, "tiles": v[3], "wait_cyc_per_tile": v[0] / v[3],
                                         "crit_cyc_per_tile": v[1] / v[3], "tail_cyc_per_tile": v[2] / v[3]})
                 rows[l]["epilogue_cycles"] = acc
+        SEL = 64 + 12 * 256 * 9                    # AVS_TRACE_SEL: phase stamps of CTA 0's lean level select
+        for l in range(n_lv):
+            v = [st.stat(f"trace:{SEL + l * 16 + i}") for i in range(6)]
+            if v[0] and v[5] and v[5] >= v[0] >= t[4 * l]:
+                rows[l]["cta0_fast_select_phases_us"] = [(v[i + 1] - v[i]) / 1e3 if v[i + 1] and v[i] else None for i in range(5)]
         out.append({"batch": b, "ms_per_search": e0.elapsed_time(e1) / 20, "levels_total": L, "levels_in_persistent_kernel": n_lv,
                     "kernel_us": (t[4 * n_lv] - t[0]) / 1e3 if n_lv else None, "per_level": rows})
     print(json.dumps({"rows": a.rows, "dim": a.dim, "k": a.k, "opts": a.opt, "trace": out}))

@@ -372,6 +372,43 @@ def test_auto_path_switches_to_tensor_cores_and_agrees_with_gemv(pkg):
         st.close()
 
 
+@pytest.mark.parametrize("n,d,nq,k,metric", [(300_000, 128, 1, 10, "COSINE"), (300_000, 128, 5, 10, "IP"), (200_000, 64, 64, 10, "COSINE"),
+                                             (150_000, 256, 130, 10, "COSINE"), (90_000, 128, 300, 5, "IP"), (400_000, 64, 2, 100, "COSINE"),
+                                             (260_000, 96, 700, 100, "COSINE"), (70_001, 128, 9, 1, "COSINE")])
+def test_boot_level_top_j_lists_match_oracle_and_the_dense_schedule(pkg, n, d, nq, k, metric):
+    """Tensor-core scan whose threshold-free level keeps the 8 best keys per half row group (boot level) instead of every
+    key: same hits as the oracle and as the dense-level schedule (option boot = 0), one launch for every level."""
+    X, ids, Q = _data(n, d, nq, seed=n % 1000 + nq, scale=(metric == "COSINE"))
+    Q[0] = X[n // 2] * 1.5                                      # a planted neighbour inside a boot-level group or not
+    st = pkg.Store(d, metric, capacity=n)
+    try:
+        st.insert(X, ids)
+        st.set_option("boot", 2)                                # default 1: batches of < 129 queries only
+        got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
+        assert st.stat("last_boot") == 1 and st.stat("last_scan_path") == 2
+        levels_boot = st.stat("last_levels")
+        exp_ids, exp_d, exp_rows = fs.search_large(X, ids, Q, k, metric)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert np.array_equal(got_rows, exp_rows)
+        st.set_option("boot", 0)
+        b_ids, b_d = st.search(Q, k)
+        assert st.stat("last_boot") == 0
+        assert np.array_equal(b_ids, got_ids) and np.array_equal(b_d, got_d)
+        assert levels_boot <= st.stat("last_levels")
+        assert st.stat("uncertified_queries") == 0 and st.stat("barrier_timeouts") == 0
+        # a row filter reaches the boot level's lists too
+        st.set_option("boot", 2)
+        allow = np.ones(n, dtype=bool)
+        allow[exp_rows[:, 0]] = False                           # ban every query's best row
+        st.set_filter(allow)
+        f_ids, f_d = st.search(Q, k)
+        assert st.stat("last_boot") == 1
+        e_ids, e_d, _ = fs.search_large(X[allow], ids[allow], Q, k, metric)
+        _check(f_ids, f_d, e_ids, e_d)
+    finally:
+        st.close()
+
+
 def test_search_json_front_end_emits_the_tts_contract(pkg, f1, tmp_path):
     """JSONL of precomputed embeddings -> the JSONL tts_with_rag.py:77-96 reads."""
     sj = load_pkg("search_json")
