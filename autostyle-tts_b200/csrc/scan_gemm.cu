@@ -158,6 +158,59 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- boot level: the 8 largest of a thread's 128 scores with sorting networks (no data-dependent control flow) ----
+#define AVS_CEX(a, b) { const float hi_ = fmaxf(a, b), lo_ = fminf(a, b); a = hi_; b = lo_; }
+// optimal 19-comparator network, descending
+__device__ __forceinline__ void boot_sort8(float (&x)[8]) {
+    AVS_CEX(x[0], x[2]) AVS_CEX(x[1], x[3]) AVS_CEX(x[4], x[6]) AVS_CEX(x[5], x[7])
+    AVS_CEX(x[0], x[4]) AVS_CEX(x[1], x[5]) AVS_CEX(x[2], x[6]) AVS_CEX(x[3], x[7])
+    AVS_CEX(x[0], x[1]) AVS_CEX(x[2], x[3]) AVS_CEX(x[4], x[5]) AVS_CEX(x[6], x[7])
+    AVS_CEX(x[2], x[4]) AVS_CEX(x[3], x[5])
+    AVS_CEX(x[1], x[4]) AVS_CEX(x[3], x[6])
+    AVS_CEX(x[1], x[2]) AVS_CEX(x[3], x[4]) AVS_CEX(x[5], x[6])
+}
+// a, b sorted descending -> a = the 8 largest of both, sorted descending (max against the reversed list, bitonic merge)
+__device__ __forceinline__ void boot_merge8(float (&a)[8], const float (&b)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], b[7 - i]);
+    AVS_CEX(a[0], a[4]) AVS_CEX(a[1], a[5]) AVS_CEX(a[2], a[6]) AVS_CEX(a[3], a[7])
+    AVS_CEX(a[0], a[2]) AVS_CEX(a[1], a[3]) AVS_CEX(a[4], a[6]) AVS_CEX(a[5], a[7])
+    AVS_CEX(a[0], a[1]) AVS_CEX(a[2], a[3]) AVS_CEX(a[4], a[5]) AVS_CEX(a[6], a[7])
+}
+// folds 32 scores into the running sorted top-8; `allow` masks rows that must not count (padding, row filter)
+__device__ __forceinline__ void boot_fold32(const uint32_t (&v)[32], uint32_t allow, bool masked, float (&top)[8]) {
+    float g[4][8];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float sc = __uint_as_float(v[8 * gi + i]) + 0.0f;   // -0 -> +0: equal values must have equal keys
+            g[gi][i] = (!masked || ((allow >> (8 * gi + i)) & 1u)) ? sc : -INFINITY;
+        }
+        boot_sort8(g[gi]);
+    }
+    boot_merge8(g[0], g[1]);
+    boot_merge8(g[2], g[3]);
+    boot_merge8(g[0], g[2]);
+    boot_merge8(top, g[0]);
+}
+// second pass: the (score, column) pairs of the scores above `v8` go to slots 0.., the first `ties_left` scores equal to
+// it (column order) to slots 7, 6, ..; `ent` = 8 slots of this thread in shared memory
+__device__ __forceinline__ void boot_emit32(const uint32_t (&v)[32], uint32_t allow, bool masked, int col0, float v8, int& pf, int& pb,
+                                            int& ties_left, uint2* ent) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float sc = __uint_as_float(v[i]) + 0.0f;
+        const bool ok = !masked || ((allow >> i) & 1u);
+        const bool gt = ok && sc > v8;
+        const bool tie = ok && sc == v8 && ties_left > 0;
+        if (gt || tie) ent[gt ? pf : pb] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + i));
+        pf += gt ? 1 : 0;
+        pb -= tie ? 1 : 0;
+        ties_left -= tie ? 1 : 0;
+    }
+}
+
 struct PipeState {
     uint32_t stage = 0, phase = 0;
     template <int N> __device__ __forceinline__ void advance() {
@@ -373,7 +426,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         auto run_tiles = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;      // 0 thresholded, 1 dense (every key stored), 2 boot (top-J per thread)
         constexpr bool DENSE = MODE == 1;
-        constexpr bool BOOT = MODE == 2;
+        constexpr bool BOOT = MODE == 2;                     // boot level, sorting networks: any number of live lanes
+        constexpr bool BOOT_FEW = MODE == 3;                 // boot level, sorted insertion: a handful of live lanes (<= 8 queries)
         for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
             const int64_t m = t / n_qblocks;
             const int qb = (int)(t - m * n_qblocks);
@@ -387,13 +441,6 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             u64* const my_cand = cand + (size_t)q * cap;
             flush_pending();
             int n_stash = 0, n_raw = 0;
-            // boot level: this thread's BOOT_J best scores of the tile half (sorted, score desc then column asc) and their columns
-            float bs[BOOT ? AVS_BOOT_J : 1];
-            int bc[BOOT ? AVS_BOOT_J : 1];
-            if constexpr (BOOT) {
-#pragma unroll
-                for (int i = 0; i < AVS_BOOT_J; ++i) { bs[i] = -INFINITY; bc[i] = -1; }
-            }
             auto reserve = [&]() {
                 pend_n = n_stash;
                 pend_dst = my_cand;
@@ -482,13 +529,16 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N + half * 128;
-            if constexpr (BOOT) {
-                // Threshold-free level without a dense store: the rank-j key (j <= BOOT_J) of everything the level visits
-                // is the rank-j key of the union of the per-thread top-J lists, and every row at or above it is in one of
-                // them.  Sorted insertion, strict compare: equal scores keep column order (smaller row first = larger
-                // key).  Lanes without a real query skip the work (batch 1: one lane of two warps).  A rolled loop over
-                // 8-column slices keeps the code small (the level is a few tiles per CTA; its speed is not the issue).
+            if constexpr (BOOT_FEW) {
+                // Boot level for at most 8 queries: one or two warps of the CTA have a live lane at all, and a lone lane
+                // inserts into its sorted top-J list only when a score beats the list's last entry (~30 times per tile),
+                // so the straightforward rolled loop costs a few microseconds where the network version costs ten.
+                // Strict compare: equal scores keep column order (smaller row first = larger key).
                 const bool live = q < plan.nq;
+                float bs[AVS_BOOT_J];
+                int bc[AVS_BOOT_J];
+#pragma unroll
+                for (int i = 0; i < AVS_BOOT_J; ++i) { bs[i] = -INFINITY; bc[i] = -1; }
 #pragma unroll 1
                 for (int c8 = 0; c8 < 128; c8 += 8) {
                     uint32_t v8[8];
@@ -502,7 +552,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         allow = vc >= 8 ? allow : (vc <= 0 ? 0u : (allow & ((1u << vc) - 1)));
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float sc = __uint_as_float(v8[i]);
+                            const float sc = __uint_as_float(v8[i]) + 0.0f;      // -0 -> +0: equal values must have equal keys
                             if (sc > bs[AVS_BOOT_J - 1] && ((allow >> i) & 1u)) {
 #pragma unroll
                                 for (int p = AVS_BOOT_J - 1; p > 0; --p) {
@@ -522,8 +572,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
                     else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
                 }
-                // slot block (group ordinal m, tile half) of the query's buffer: BOOT_J keys, 0 = empty
-                if (live) {
+                if (live) {   // slot block (group ordinal m, tile half): BOOT_J keys, best first, 0 = empty
                     ulonglong2* dst = reinterpret_cast<ulonglong2*>(my_cand + ((size_t)m * 2 + half) * AVS_BOOT_J);
 #pragma unroll
                     for (int i = 0; i < AVS_BOOT_J; i += 2) {
@@ -531,6 +580,103 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         kk.x = bc[i] >= 0 ? avs_make_key(bs[i], (uint32_t)(row0 + bc[i])) : 0ull;
                         kk.y = bc[i + 1] >= 0 ? avs_make_key(bs[i + 1], (uint32_t)(row0 + bc[i + 1])) : 0ull;
                         dst[i >> 1] = kk;
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            if constexpr (BOOT) {
+                // Threshold-free level without a dense store: the rank-j key (j <= BOOT_J) of everything the level visits
+                // is the rank-j key of the union of the per-thread top-J sets, and every row at or above it is in one of
+                // them.  Pass 1 folds the thread's 128 scores into their 8 largest VALUES with sorting networks (fmax /
+                // fmin only: no divergence however many lanes are live); pass 2 reads the accumulator again and keeps the
+                // rows above the 8th value plus as many rows equal to it (column order = key order) as complete the eight.
+                const bool warp_live = q - lane < plan.nq;        // warps without a real query only hand the accumulator back
+                const bool masked = has_pad || filt != nullptr;
+                uint2* const ent = reinterpret_cast<uint2*>(my_raw);          // 8 (score bits, column) slots of this thread
+                if (warp_live) {
+                    uint32_t allow[4] = {~0u, ~0u, ~0u, ~0u};
+                    if (masked) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t a = filt ? filt[(row0 + 32 * c) >> 5] : ~0u;
+                            const int vc = valid_cols - 32 * c;
+                            allow[c] = vc >= 32 ? a : (vc <= 0 ? 0u : (a & ((1u << vc) - 1)));
+                        }
+                    }
+                    float top[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { top[i] = -INFINITY; ent[i] = make_uint2(0u, 0xFFFFFFFFu); }
+                    uint32_t va[32], vb[32];
+                    __syncwarp();
+                    tmem_ld32(t_base, va);
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 32, vb);
+                    boot_fold32(va, allow[0], masked, top);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 64, va);
+                    boot_fold32(vb, allow[1], masked, top);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 96, vb);
+                    boot_fold32(va, allow[2], masked, top);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base, va);
+                    boot_fold32(vb, allow[3], masked, top);
+                    const float v8 = top[7];
+                    int n_gt = 0;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) n_gt += top[i] > v8 ? 1 : 0;
+                    int pf = 0, pb = 7, ties_left = 8 - n_gt;
+                    if (!(v8 > -INFINITY)) ties_left = 0;      // fewer than 8 real rows: nothing ties with the empty value
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 32, vb);
+                    boot_emit32(va, allow[0], masked, 0, v8, pf, pb, ties_left, ent);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 64, va);
+                    boot_emit32(vb, allow[1], masked, 32, v8, pf, pb, ties_left, ent);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tmem_ld32(t_base + 96, vb);
+                    boot_emit32(va, allow[2], masked, 64, v8, pf, pb, ties_left, ent);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
+                        else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
+                    }
+                    boot_emit32(vb, allow[3], masked, 96, v8, pf, pb, ties_left, ent);
+                    // slot block (group ordinal m, tile half) of the query's buffer: BOOT_J keys, the best one first, 0 = empty
+                    if (q < plan.nq) {
+                        u64 kk[8];
+                        u64 best = 0ull;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint2 e = ent[i];
+                            kk[i] = e.y != 0xFFFFFFFFu ? avs_make_key(__uint_as_float(e.x), (uint32_t)(row0 + (int)e.y)) : 0ull;
+                            best = kk[i] > best ? kk[i] : best;
+                        }
+                        // the best key goes to slot 0 (the level select reads the slot-0 keys first): swap it with whatever sits there
+                        const u64 first = kk[0];
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) kk[i] = kk[i] == best ? first : kk[i];
+                        kk[0] = best;
+                        ulonglong2* dst = reinterpret_cast<ulonglong2*>(my_cand + ((size_t)m * 2 + half) * AVS_BOOT_J);
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) dst[i >> 1] = make_ulonglong2(kk[i], kk[i + 1]);
+                    }
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 1 || leader) mbar_arrive(smem_u32(tempty_bar + acc));
+                        else mbar_arrive_remote(smem_u32(tempty_bar + acc), 0);
                     }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -565,7 +711,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         };
-        if (lv.dense == 2) run_tiles(std::integral_constant<int, 2>{});
+        if (lv.dense == 2 && plan.nq <= 8) run_tiles(std::integral_constant<int, 3>{});
+        else if (lv.dense == 2) run_tiles(std::integral_constant<int, 2>{});
         else if (lv.dense == 1) run_tiles(std::integral_constant<int, 1>{});
         else run_tiles(std::integral_constant<int, 0>{});
         flush_pending();
@@ -591,7 +738,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
             } else {
                 for (int q = blockIdx.x * 8 + (warp - 4); q < plan.nq; q += gridDim.x * 8)
-                    warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list);
+                    warp_select_level(plan, q, lane, plan.j_rank[l], final_level, dense_total, plan.k_eps[l], list, lv.dense == 2);
             }
         }
         stamp(3 + 4 * l);                              // this CTA's share of the selects is done

@@ -1270,14 +1270,18 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     // must not exceed J: the sparsest ratio is raised until it does not; stores too small for that keep the dense level.
     bool boot = false;
     // (a store the warp-dot path searches in ONE dense level keeps that path: nothing to save there)
-    // boot = 1 (default): HBM-bound batches only (coarse schedule) - the boot epilogue (sorted insertion of 128 scores per
-    // thread and tile, ~15 us with every lane live) hides behind the 8.5 us a tile takes to stream only when few lanes
-    // are live or few tiles are scanned; measured at batch 1024 it cost 45 us more than the dense 2 048-row level.  boot = 2: always.
-    const bool boot_wanted = s->opt_boot == 2 || (s->opt_boot == 1 && nq < s->opt_fine_min_batch);
+    const bool boot_wanted = s->opt_boot != 0;
     if (boot_wanted && gemm_eligible && !(hybrid_legacy && s->count <= (int64_t)s->opt_dense_rows)) {
         use_gemm = true; hybrid = false;              // with a boot level the tensor-core scan takes every level, small batches too
         fine_levels = nq >= s->opt_fine_min_batch;
-        const int64_t boot_groups = cap / (2 * AVS_BOOT_J);
+        // room for cap / (2 J) groups; the compute-bound schedule keeps the level to ~4 tiles per CTA pair and query block
+        // sweep (its epilogue, ~10 us a tile, is slower than the MMA of the tile)
+        int64_t boot_groups = cap / (2 * AVS_BOOT_J);
+        if (fine_levels) {
+            const int64_t n_qb = (nq + 255) / 256, pairs = s->num_sms / 2;
+            const int64_t g = (4 * pairs + n_qb - 1) / n_qb;
+            if (g < boot_groups) boot_groups = g < 8 ? 8 : g;
+        }
         // HBM-bound batches: a level costs two grid barriers and a select, an accepted row next to nothing - allow a
         // sparser boot level (up to cap / 32: 8 * ratio expected survivors fill a quarter of the buffer at most)
         int64_t rho_boot = rho;
@@ -1288,7 +1292,9 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
             strides[1] = fine_levels ? s->opt_fine_ratio : 2;
             L = 2;
         }
-        if (L >= 2 && !(fine_levels && L == 2 && s->eps_rule)) {   // the eps rule asks the last select for rank k > J
+        // the eps rule asks the select in front of the final level for rank k > J: that must not be the boot level's
+        if (fine_levels && L == 2 && s->eps_rule) { strides[2] = strides[1] * 2; L = 3; }
+        if (L >= 2) {
             for (int it = 0; it < 64; ++it) {
                 set_ranks();
                 if (j_ranks[0] <= AVS_BOOT_J) break;
@@ -1525,7 +1531,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "final_sigma") s->opt_final_sigma = value < 1 ? 1 : (int)value;
     else if (k == "fine_ratio") s->opt_fine_ratio = value < 2 ? 2 : (int)value;
     else if (k == "hybrid") s->opt_hybrid = value != 0;
-    else if (k == "boot") s->opt_boot = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+    else if (k == "boot") s->opt_boot = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));

@@ -172,7 +172,7 @@ __device__ __forceinline__ void wsel_small(const WarpSelectArgs& a, int q, int l
 
 // `list`: 256 u64 of shared memory owned by this warp (also used as a 256-bin int histogram by the radix path).
 __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, int lane, int j_rank, bool is_final,
-                                               int dense_total, int k_eps, u64* list) {
+                                               int dense_total, int k_eps, u64* list, bool boot_lists = false) {
     u64* c = a.cand + (size_t)q * a.cap;
     const int total_in = dense_total > 0 ? dense_total : a.cnt[q];
     const bool lost = dense_total == 0 && total_in > a.cap;       // more keys were offered than the buffer holds
@@ -185,7 +185,45 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
     // compacted into the warp's list and then take the register-sort path below
     const u64* src = c;
     int n_src = n;
-    if (n > 256 && dense_total > 0 && !is_final && jj <= 32 && k_eps == 0) {   // eps rule: the threshold may end up below the pivot
+    // ---- boot level (lists of 8 keys, the best one in slot 0): pivot from the list heads alone ----
+    // the rank-j value of the 32 lane maxima over the HEADS is a lower bound of the rank-j key; a key at or above it sits
+    // in a list whose head is at or above it - a handful of lists.  One pass over an eighth of the keys, then those lists.
+    bool heads_done = false;
+    if (boot_lists && n > 256 && !is_final && jj <= 32 && k_eps == 0) {
+        const int n_lists = n >> 3;
+        u64 lm = 0;
+#pragma unroll 8
+        for (int l = lane; l < n_lists; l += 32) { const u64 key = c[8 * l]; lm = key > lm ? key : lm; }
+        u64 k1[1] = {lm};
+        wsel_sort_desc<1>(k1, lane);
+        const u64 P = __shfl_sync(0xffffffffu, k1[0], jj - 1);
+        if (P != 0ull) {
+            int m = 0;
+            for (int l0 = 0; l0 < n_lists; l0 += 32) {
+                const int l = l0 + lane;
+                const bool hot = l < n_lists && c[8 * l] >= P;
+                if (__any_sync(0xffffffffu, hot)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const u64 key = hot ? c[8 * l + i] : 0ull;
+                        const bool in = key >= P;
+                        const unsigned bal = __ballot_sync(0xffffffffu, in);
+                        const int pos = m + __popc(bal & ((1u << lane) - 1));
+                        if (in && pos < 256) list[pos] = key;
+                        m += __popc(bal);
+                    }
+                }
+            }
+            __syncwarp();
+            if (m <= 256) { src = list; n_src = m; heads_done = true; }   // m >= jj by construction
+        }
+    }
+    if (heads_done) {
+        // fall through to the register select on `list`
+    } else
+    // (also for a thresholded level that collected more than 256 keys - the tail of the survivor-count distribution: one
+    // such query among a thousand would otherwise send its warp through the 8-pass radix select while the grid waits)
+    if (n > 256 && !lost && !is_final && jj <= 32 && k_eps == 0) {   // eps rule: the threshold may end up below the pivot
         u64 lm = 0;
 #pragma unroll 8
         for (int i = lane; i < n; i += 32) { const u64 key = c[i]; lm = key > lm ? key : lm; }   // 8 loads in flight per lane

@@ -261,10 +261,14 @@ def ncu_traffic(rows, dim, k, batch, path, world):
     if not key or not files:
         return None, "no committed ncu capture for this kernel variant"
     try:
-        ent = json.load(open(files[-1]))[key]
-        return ent["dram_bytes_per_launch"], f"ncu --set full capture of this workload, {os.path.relpath(files[-1], ROOT)} [{key}]"
+        table = json.load(open(files[-1]))
     except Exception:
         return None, "traffic.json unreadable"
+    if key not in table:
+        return None, f"no committed ncu capture for this kernel variant in {os.path.relpath(files[-1], ROOT)}"
+    return (table[key]["dram_bytes_per_launch"],
+            f"ncu --set full capture of this workload with this round's kernels (not measured in this run: ncu cannot run under the "
+            f"driver), {os.path.relpath(files[-1], ROOT)} [{key}]")
 
 
 # ------------------------------------------------------------------------------------------------

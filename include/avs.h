@@ -133,10 +133,9 @@ int avs_p2p_init(avs_store* s, int rank, int world, void* handle64_out);
 int avs_p2p_connect(avs_store* s, const void* handles, int world);
 
 /* Options: "scan_path" 0=auto 1=gemv 2=gemm; "hybrid" 0|1 (auto mode, <= 8 queries: dense warp-dot level, tensor-core
- * scan for the later levels; default 1 - only used where the boot level below does not apply); "boot" 0|1|2 (tensor-core
+ * scan for the later levels; default 1 - only used where the boot level below does not apply); "boot" 0|1 (tensor-core
  * scan: the threshold-free level keeps the 8 best keys of every half row group instead of storing every key, so it
- * may visit up to 32 K rows and every level runs in the ONE persistent launch; 1 = for HBM-bound batches (fewer than
- * "fine_min_batch" queries; default), 2 = always, 0 = never);
+ * may visit up to 32 K rows and every level of every batch size runs in the ONE persistent launch; default 1);
  * "p2p_timeout_ms" (wall-clock bound of a wait for a peer in the exchange kernels, default 120000);
  * "oversample" K' override (0=auto); "gemm_min_batch";
  * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant) and "cta_group_small" 1|2 (the variant for batches of at most

@@ -383,7 +383,6 @@ def test_boot_level_top_j_lists_match_oracle_and_the_dense_schedule(pkg, n, d, n
     st = pkg.Store(d, metric, capacity=n)
     try:
         st.insert(X, ids)
-        st.set_option("boot", 2)                                # default 1: batches of < 129 queries only
         got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
         assert st.stat("last_boot") == 1 and st.stat("last_scan_path") == 2
         levels_boot = st.stat("last_levels")
@@ -397,7 +396,7 @@ def test_boot_level_top_j_lists_match_oracle_and_the_dense_schedule(pkg, n, d, n
         assert levels_boot <= st.stat("last_levels")
         assert st.stat("uncertified_queries") == 0 and st.stat("barrier_timeouts") == 0
         # a row filter reaches the boot level's lists too
-        st.set_option("boot", 2)
+        st.set_option("boot", 1)
         allow = np.ones(n, dtype=bool)
         allow[exp_rows[:, 0]] = False                           # ban every query's best row
         st.set_filter(allow)
