@@ -33,7 +33,7 @@ from .engine import AvsError, Store
 from .filter_expr import compile_filter
 from .schema import CollectionSchema, DataType, FieldSchema, IndexParams, MilvusException
 
-MAX_LIMIT = 256  # largest `limit` the fused top-k pipeline serves (avs.h)
+MAX_LIMIT = 16384  # MilvusClient's own ceiling; limits above 256 take the exact fp32 master scan (include/avs.h)
 
 
 class _Collection:

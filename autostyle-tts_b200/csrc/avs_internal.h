@@ -16,6 +16,7 @@ typedef unsigned long long u64;
 #define AVS_GROUP_ROWS 256      // sampling / tiling granularity of the scan (rows)
 #define AVS_MAX_KPRIME 256      // largest oversampled candidate list
 #define AVS_REPAIR_CAP 4096     // largest exact-repair slice per flagged query (rows tied at the k-th score beyond it: uncertified)
+#define AVS_MAX_LIMIT 16384     // largest `limit` (MilvusClient's own); limits above AVS_MAX_KPRIME are served by the exact master scan
 #define AVS_MAX_LEVELS 12
 #define AVS_DENSE_CAP 65536      // rows of the threshold-free level of the gemv path (dense key buffer per query)
 #define AVS_DENSE_MAX_NQ 64      // the dense buffer is kept for this many queries
@@ -39,6 +40,30 @@ void avs_set_error(const char* fmt, ...);
         int _r = (expr);                                                                       \
         if (_r != AVS_OK) return _r;                                                           \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The kernels of one search form a chain prep -> scan -> finalize -> wide -> repair.  Each is launched with the
+// programmatic-stream-serialization attribute, raises `launch_dependents` first thing (its successor's CTAs may then be
+// staged on whatever SM resources are free and run their own set-up) and executes `griddepcontrol.wait` - every
+// thread, before any early exit and before it touches global memory a predecessor writes - which returns once the
+// predecessor grid has completed and its writes are visible.  A kernel that skipped the wait could complete before
+// its predecessor and break the chain's transitivity for ITS successor, hence "every thread, unconditionally".
+#ifdef __CUDACC__
+__device__ __forceinline__ void avs_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void avs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t avs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- order-preserving keys ------------------------------------------------------------------
 // key = (monotone(float score) << 32) | (0xFFFFFFFF - row): a larger key is a better
@@ -96,6 +121,7 @@ struct AvsScanPlan {
     int n_levels;                       // levels scanned by this launch
     int last_is_final;                  // its last level is the final level of the search (select -> top K' + bound)
     int nq, kprime, cap;
+    int prefetch;                       // HBM-bound batches: L2 prefetch distance of the TMA producer in k-blocks (0: off)
     int64_t n_eff;                      // rows that may be returned (filter-allowed count)
     AvsLevel lv[AVS_MAX_LEVELS];
     int j_rank[AVS_MAX_LEVELS];
@@ -199,6 +225,8 @@ struct avs_store {
     int opt_finalize_threads = 0;    // 0: 1024 threads per query up to 64 queries, 256 beyond
     int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
+    int opt_l2_prefetch = 0;         // tensor-core scan, a single query block: L2 prefetch distance in k-blocks (0: off)
+    int opt_pdl = 1;                 // programmatic dependent launch between the kernels of a search
     int rank = 0, world = 1;
 };
 

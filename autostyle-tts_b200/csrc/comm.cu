@@ -479,6 +479,7 @@ extern "C" int avs_search_sharded(avs_store* s, const float* q, int nq, int k, i
     const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
     if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
     if (s->filter) { avs_set_error("avs_search_sharded: row filters are not supported on a sharded store"); return AVS_E_STATE; }
+    if (k > AVS_MAX_KPRIME) { avs_set_error("avs_search_sharded: limit %d above %d is served on unsharded stores only", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     // local exact top-k; ids/scores land in the caller's buffers first and are then replaced
     AVS_CHECK(avs_search_local(s, q, nq, k, out_ids, out_scores, nullptr, st));
@@ -500,6 +501,7 @@ extern "C" int avs_search_sharded_host(avs_store* s, const float* q_host, int nq
     const bool use_p2p = p2p && p2p->connected && s->opt_p2p && (size_t)nq * k <= P2P_ITEMS_PER_SRC && nq <= P2P_MAX_NQ;
     if (!use_p2p && !s->nccl_comm) { avs_set_error("avs_search_sharded_host: neither avs_comm_init nor avs_p2p_connect has been called on this store"); return AVS_E_STATE; }
     if (s->filter) { avs_set_error("avs_search_sharded_host: row filters are not supported on a sharded store"); return AVS_E_STATE; }
+    if (k > AVS_MAX_KPRIME) { avs_set_error("avs_search_sharded_host: limit %d above %d is served on unsharded stores only", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
     AVS_CUDA(cudaSetDevice(s->device));
     AVS_CHECK(avs_host_staging_reserve(s, nq, k));
     AvsScratch& c = s->sc;

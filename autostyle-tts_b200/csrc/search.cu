@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
                                                            int* __restrict__ flagged, int* __restrict__ flagged2,
                                                            unsigned int* __restrict__ gbar) {
     __shared__ double sh[4];
+    avs_pdl_trigger();                         // the scan kernel may be staged and run its set-up while the queries are prepared
     const int qi = blockIdx.x;
     if (qi == 0 && threadIdx.x == 0) { flagged[0] = 0; flagged2[0] = 0; }   // repair queues of this search start empty
     if (qi == 0 && threadIdx.x < 4) gbar[threadIdx.x] = 0u;                 // grid-barrier counters of the persistent kernels
@@ -591,9 +592,43 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
                                                        double* __restrict__ rep_thr, int* __restrict__ rep_cnt,
                                                        u64* __restrict__ dstat) {
     __shared__ Hit sm[AVS_MAX_KPRIME];
+    __shared__ u64 s_keys[AVS_MAX_KPRIME];
+    __shared__ uint32_t s_live[AVS_MAX_KPRIME];
+    __shared__ double s_cut;
+    __shared__ int s_nlive;
+    avs_pdl_trigger();
+    avs_pdl_wait();                            // the scan (and, through it, prep) has completed
     const int q = blockIdx.x, t = threadIdx.x;
     const int n = topn[q];
-    {   // K5: exact float64 rescoring, one warp per candidate (8 warps take the K' candidates in turns)
+    const int need = (int64_t)k < n_rows ? k : (int)n_rows;
+    // Which candidates can still reach the top-k?  With s_k the `need`-th best SCAN score of the list, `need` rows have
+    // exact score >= s_k - eps, and a candidate whose scan score is below s_k - 2 eps has exact score < s_k - eps: it
+    // cannot be among the `need` best and its 3 KB master row need not be fetched (C2: ~40 % of K' = 32).  The list
+    // arrives unordered from the radix selects, so every key's rank is counted (K' <= 256 broadcast reads).
+    if (t < kprime) s_keys[t] = t < n ? topkeys[(size_t)q * kprime + t] : 0ull;
+    if (t == 0) { s_cut = -INFINITY; s_nlive = 0; }
+    __syncthreads();
+    int my_rank = -1;
+    u64 my_key = 0ull;
+    if (t < kprime) {
+        my_key = s_keys[t];
+        if (my_key != 0ull) {
+            int r = 0;
+            for (int j = 0; j < kprime; ++j) r += s_keys[j] > my_key ? 1 : 0;
+            my_rank = r;
+            if (r == need - 1) s_cut = (double)avs_key_score(my_key) - 2.0 * (double)eps[q];
+        }
+    }
+    __syncthreads();
+    if (my_rank >= 0 && (my_rank < need || (double)avs_key_score(my_key) >= s_cut)) {   // the live set is a prefix in rank order
+        s_live[my_rank] = avs_key_row(my_key);
+        atomicMax(&s_nlive, my_rank + 1);
+    }
+    __syncthreads();
+    const int n_live = s_nlive;
+    int P = 2;
+    while (P < n_live) P <<= 1;                // sorted size; P <= K'
+    {   // K5: exact float64 rescoring, one warp per candidate (8 warps take the live candidates in turns)
         const int lane = t & 31, warp = t >> 5;
         const double qn = qnorm[q];
         const float* qp = qraw + (size_t)q * dim;
@@ -601,29 +636,33 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
         const bool vec = ((dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(qp)) & 15) == 0;
         if (THREADS <= 256 && vec && kprime >= 4 * nwarps) {
             // four candidates per warp at a time: their row loads overlap, the query is loaded once for the four
-            for (int c0 = warp * 4; c0 < kprime; c0 += 4 * nwarps) {
+            for (int c0 = warp * 4; c0 < P; c0 += 4 * nwarps) {
+                if (c0 >= n_live) {
+                    if (lane < 4 && c0 + lane < P) { Hit h; h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; sm[c0 + lane] = h; }
+                    continue;
+                }
                 uint32_t rows4[4];
                 const float* xr[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    rows4[i] = c0 + i < n ? avs_key_row(topkeys[(size_t)q * kprime + c0 + i]) : 0u;   // row 0 stands in for padding slots
+                    rows4[i] = s_live[c0 + i < n_live ? c0 + i : c0];   // the group's first row stands in for padding slots
                     xr[i] = master + (size_t)rows4[i] * dim;
                 }
                 double sc4[4];
                 exact_score_rows<4>(xr, qp, dim, qn, metric, lane, sc4);
-                if (lane < 4) {
+                if (lane < 4 && c0 + lane < P) {
                     Hit h;
                     const int c = c0 + lane;
-                    if (c < n) { h.row = rows4[lane]; h.s = sc4[lane]; h.id = ids[h.row]; }
+                    if (c < n_live) { h.row = rows4[lane]; h.s = sc4[lane]; h.id = ids[h.row]; }
                     else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
                     sm[c] = h;
                 }
             }
         } else {
-        for (int c = warp; c < kprime; c += nwarps) {
+        for (int c = warp; c < P; c += nwarps) {
             Hit h;
-            if (c < n) {
-                h.row = avs_key_row(topkeys[(size_t)q * kprime + c]);
+            if (c < n_live) {
+                h.row = s_live[c];
                 h.s = exact_score(master + (size_t)h.row * dim, qp, dim, qn, metric, lane);
                 h.id = ids[h.row];
             } else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
@@ -632,9 +671,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
         }
     }
     __syncthreads();
-    for (int k2 = 2; k2 <= kprime; k2 <<= 1) {
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-            if (t < kprime) {
+            if (t < P) {
                 const int ixj = t ^ j;
                 if (ixj > t) {
                     const bool desc = (t & k2) == 0;
@@ -646,14 +685,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
         }
     }
     if (t < k) {
-        const bool valid = t < n;
+        const bool valid = t < n_live;
         out_ids[(size_t)q * k + t] = valid ? sm[t].id : -1;
         out_scores[(size_t)q * k + t] = valid ? (float)sm[t].s : -INFINITY;
         if (out_rows) out_rows[(size_t)q * k + t] = valid ? (int64_t)sm[t].row : -1;
         out_s64[(size_t)q * k + t] = valid ? sm[t].s : -INFINITY;
     }
     if (t == 0) {
-        const int need = (int64_t)k < n_rows ? k : (int)n_rows;
         const float b = bound[q];
         bool ok = n >= need;
         if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
@@ -686,6 +724,8 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
                                                             int* __restrict__ rep_cnt, u64* __restrict__ dstat) {
     extern __shared__ unsigned char raw[];
     Hit* sm = reinterpret_cast<Hit*>(raw);
+    avs_pdl_trigger();
+    avs_pdl_wait();                            // finalize has completed: the queue of flagged queries is final
     const int nf = flagged[0];
     const int f = blockIdx.x;
     if (f >= nf) return;
@@ -780,6 +820,8 @@ __global__ void __launch_bounds__(1024) wide_rescore_kernel(const float* __restr
 struct RepairArgs {
     const float* master; const float* q; const double* qnorm; const int64_t* ids; const uint32_t* filt;
     int64_t n_rows, n_eff; int dim, metric, k, group;
+    int slice_max;                                                        // largest slice per flagged query: AVS_REPAIR_CAP, or up to
+                                                                          // AVS_LARGE_SLICE_MAX (a power of two) for limits > AVS_MAX_KPRIME
     const int* flagged2; double* rep_thr; int* rep_cnt; int* rep_sel;     // rep_sel: [nq][2] histogram bin / rows above it
     double* pool_s; uint32_t* pool_row; int64_t pool_items;
     unsigned int* hist;                                                   // [REPAIR_GMAX][REPAIR_BINS]
@@ -865,19 +907,22 @@ __device__ __forceinline__ void exact_scores_group(const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(REPAIR_THREADS) repair_kernel(RepairArgs a) {
     extern __shared__ unsigned char raw[];
+    avs_pdl_wait();                            // wide rescoring has completed
     int nf = a.flagged2[0];
     if (nf == 0) return;                                                  // uniform: nobody reaches a barrier
     __shared__ double s_thr[REPAIR_GMAX], s_qn[REPAIR_GMAX];
     __shared__ int s_f[REPAIR_GMAX], s_q[REPAIR_GMAX], s_bin[REPAIR_GMAX];
     const int need = (int64_t)a.k < a.n_eff ? a.k : (int)a.n_eff;
-    const int64_t nf_max = a.pool_items / AVS_MAX_KPRIME;
+    const bool large = a.slice_max > AVS_REPAIR_CAP;                      // slices beyond shared memory: sorted in place in the pool
+    const int64_t nf_max = a.pool_items / (large ? a.slice_max : AVS_MAX_KPRIME);
     if (nf > nf_max) {                                                    // more flagged queries than the pool has minimal slices for
         if (blockIdx.x == 0)
             for (int f = (int)nf_max + threadIdx.x; f < nf; f += blockDim.x) { a.status[a.flagged2[1 + f]] |= ST_UNCERTIFIED; atomicAdd(a.dstat + 1, 1ull); }
         nf = (int)nf_max;
     }
     int capq = (int)(a.pool_items / nf);
-    if (capq > AVS_REPAIR_CAP) capq = AVS_REPAIR_CAP;
+    if (capq > a.slice_max) capq = a.slice_max;
+    if (large) { int p2 = 1; while (p2 * 2 <= capq) p2 *= 2; capq = p2; }   // the in-place bitonic sort needs a power of two
     unsigned int epoch = 0;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (int64_t)blockIdx.x * (REPAIR_THREADS / 32) + (threadIdx.x >> 5);
@@ -1007,6 +1052,46 @@ __global__ void __launch_bounds__(REPAIR_THREADS) repair_kernel(RepairArgs a) {
         }
         int P = 32;
         while (P < total) P <<= 1;
+        if (P > AVS_REPAIR_CAP) {
+            // Limits beyond 2 K rows (MilvusClient allows 16 384): the slice does not fit shared memory, so the CTA sorts
+            // it where it lies - same network, same order (score desc, id asc, row asc); the ids are only looked up when two
+            // scores are equal.  ~120 network stages over L2-resident data: well under a millisecond per query.
+            double* ps = a.pool_s + (size_t)f * capq;
+            uint32_t* pr = a.pool_row + (size_t)f * capq;
+            for (int i = total + threadIdx.x; i < P; i += blockDim.x) { ps[i] = -INFINITY; pr[i] = 0xFFFFFFFFu; }
+            __syncthreads();
+            for (int k2 = 2; k2 <= P; k2 <<= 1) {
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const bool desc = (i & k2) == 0;
+                            const double sx = ps[i], sy = ps[ixj];
+                            const uint32_t rx = pr[i], ry = pr[ixj];
+                            bool x_better;                           // hit_better(x, y)
+                            if (sx != sy) x_better = sx > sy;
+                            else {
+                                const int64_t ix = rx == 0xFFFFFFFFu ? INT64_MAX : a.ids[rx], iy = ry == 0xFFFFFFFFu ? INT64_MAX : a.ids[ry];
+                                x_better = ix != iy ? ix < iy : rx < ry;
+                            }
+                            const bool same = sx == sy && rx == ry;  // two padding entries
+                            if (!same && (desc ? !x_better : x_better)) { ps[i] = sy; pr[i] = ry; ps[ixj] = sx; pr[ixj] = rx; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int t = threadIdx.x; t < a.k; t += blockDim.x) {
+                const bool valid = t < total;
+                const uint32_t r = valid ? pr[t] : 0u;
+                a.out_ids[(size_t)q * a.k + t] = valid ? a.ids[r] : -1;
+                a.out_scores[(size_t)q * a.k + t] = valid ? (float)ps[t] : -INFINITY;
+                if (a.out_rows) a.out_rows[(size_t)q * a.k + t] = valid ? (int64_t)r : -1;
+                a.out_s64[(size_t)q * a.k + t] = valid ? ps[t] : -INFINITY;
+            }
+            if (threadIdx.x == 0) atomicAdd(a.dstat + 0, 1ull);
+            continue;
+        }
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
             Hit h;
             if (i < total) { h.s = a.pool_s[(size_t)f * capq + i]; h.row = a.pool_row[(size_t)f * capq + i]; h.id = a.ids[h.row]; }
@@ -1046,6 +1131,15 @@ __global__ void fill_empty_kernel(int64_t* ids, float* scores, int64_t* rows, do
         if (rows) rows[i] = -1;
         if (s64) s64[i] = -INFINITY;
     }
+}
+
+// Limits above AVS_MAX_KPRIME: every query of the chunk [q0, q0 + n) goes straight to the exact repair kernel, without a
+// bound (it locates the k-th best score itself with two histogram passes over the float64 scores).
+__global__ void large_k_mark_kernel(int q0, int n, int* __restrict__ flagged2, double* __restrict__ rep_thr,
+                                    int* __restrict__ rep_cnt, unsigned int* __restrict__ gbar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { flagged2[0] = n; gbar[1] = 0u; }
+    if (i < n) { flagged2[1 + i] = q0 + i; rep_thr[i] = -INFINITY; rep_cnt[i] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1174,7 +1268,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
                      int64_t* out_rows, cudaStream_t st) {
     if (!s) { avs_set_error("avs_search: NULL store"); return AVS_E_INVALID; }
     if (nq < 0 || (nq > 0 && (!q || !out_ids || !out_scores))) { avs_set_error("avs_search: NULL query/output buffer"); return AVS_E_INVALID; }
-    if (k < 1 || k > AVS_MAX_KPRIME) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
+    if (k < 1 || k > AVS_MAX_LIMIT) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_LIMIT); return AVS_E_INVALID; }
     if (nq == 0) return AVS_OK;
     if (nq > (1 << 20)) { avs_set_error("avs_search: more than 2^20 queries in one call"); return AVS_E_INVALID; }
     AVS_CUDA(cudaSetDevice(s->device));
@@ -1185,6 +1279,10 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     if (kprime < 16) kprime = 16;
     if (kprime > AVS_MAX_KPRIME) kprime = AVS_MAX_KPRIME;
     if (kprime < k) kprime = pow2ceil(k);
+    // Limits above AVS_MAX_KPRIME (MilvusClient allows 16 384; the reference never asks for more than 5) skip the bf16
+    // scan altogether: the exact repair kernel serves them from the fp32 master (below).  Minimal scan scratch.
+    const bool large_k = k > AVS_MAX_KPRIME;
+    if (large_k) kprime = 16;
     int cap = pow2ceil(48 * kprime);
     if (cap < 1024) cap = 1024;
     if (cap > 16384) cap = 16384;
@@ -1375,6 +1473,40 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         s->rep_smem_seen = rep_smem;
     }
 
+    if (large_k) {
+        // slice per query: room for 2 k rows (ties inside the last histogram bin of the threshold search), a power of two;
+        // the pool serves pool / slice queries per launch (at least 32), the kernel takes them 8 per pass over the master
+        int slice = pow2ceil(2 * k);
+        if (slice < AVS_REPAIR_CAP) slice = AVS_REPAIR_CAP;
+        int chunk = (int)(c.pool_items / (size_t)slice);
+        if (chunk < 1) { avs_set_error("avs_search: repair pool too small for limit %d", k); return AVS_E_STATE; }
+        const int64_t n_out = (int64_t)nq * k;
+        fill_empty_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(out_ids, out_scores, out_rows, c.out_s64, n_out);
+        s->st_launches++;
+        for (int q0 = 0; q0 < nq; q0 += chunk) {
+            const int n = nq - q0 < chunk ? nq - q0 : chunk;
+            large_k_mark_kernel<<<(n + 255) / 256, 256, 0, st>>>(q0, n, c.flagged2, c.rep_thr, c.rep_cnt, c.gbar);
+            RepairArgs ra;
+            ra.master = s->master; ra.q = q; ra.qnorm = c.qnorm; ra.ids = s->ids; ra.filt = s->filter;
+            ra.n_rows = s->count; ra.n_eff = n_eff; ra.dim = s->dim; ra.metric = s->metric; ra.k = k; ra.group = rep_group;
+            ra.slice_max = slice;
+            ra.flagged2 = c.flagged2; ra.rep_thr = c.rep_thr; ra.rep_cnt = c.rep_cnt; ra.rep_sel = c.rep_sel;
+            ra.pool_s = c.rep_s; ra.pool_row = c.rep_row; ra.pool_items = (int64_t)c.pool_items; ra.hist = c.rep_hist;
+            ra.out_ids = out_ids; ra.out_scores = out_scores; ra.out_rows = out_rows; ra.out_s64 = c.out_s64; ra.status = c.status;
+            ra.dstat = s->dstat; ra.gbar = c.gbar + 1; ra.err = reinterpret_cast<unsigned int*>(s->dstat + 3);
+            void* args[] = {&ra};
+            AVS_CUDA(cudaLaunchCooperativeKernel((const void*)repair_kernel, dim3((unsigned)(rep_ctas_per_sm[s->device & 63] * s->num_sms)),
+                                                 dim3(REPAIR_THREADS), args, rep_smem, st));
+            s->st_launches += 2;
+        }
+        s->st_last_path = 3;                 // exact master scan
+        s->st_last_levels = 0;
+        s->st_last_final_rows = s->count;
+        AVS_CUDA(cudaEventRecord(pev, st));
+        if (s->h_stats) AVS_CUDA(cudaMemcpyAsync(s->h_stats, s->dstat, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        return AVS_OK;
+    }
+
     // Level schedule -> launches.  Tensor-core path: ONE persistent launch scans every level and runs the selects
     // between them (scan_gemm.cu).  Hybrid small-batch path: warp-dot dense level + its select, then one persistent
     // launch for the remaining levels.  Warp-dot path: a scan and a select launch per level.
@@ -1399,6 +1531,7 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         plan.n_levels = L - first_gemm_level;
         plan.last_is_final = 1;
         plan.nq = nq; plan.kprime = kprime; plan.cap = cap; plan.n_eff = n_eff;
+        plan.prefetch = s->opt_l2_prefetch;
         int64_t rows_scanned = 0;
         for (int l = first_gemm_level; l < L; ++l) {
             const int i = l - first_gemm_level;
@@ -1420,33 +1553,42 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
     }
 
     const int fin_threads = s->opt_finalize_threads > 0 ? s->opt_finalize_threads : (nq <= 64 ? 1024 : 256);
+    // finalize -> wide -> repair: programmatic dependent launches (every kernel waits for its predecessor on the
+    // device before it reads anything; what is saved is the launch latency between them)
+    const bool pdl = s->opt_pdl != 0;
     if (fin_threads == 256)
-        finalize_kernel<256><<<nq, 256, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
-                                                 n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
-                                                 c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
+        AVS_CUDA(avs_launch(finalize_kernel<256>, dim3(nq), dim3(256), 0, st, pdl,
+                            s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
+                            n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
+                            c.flagged, c.rep_thr, c.rep_cnt, s->dstat));
     else
-        finalize_kernel<1024><<<nq, fin_threads, 0, st>>>(s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
-                                                          n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
-                                                          c.flagged, c.rep_thr, c.rep_cnt, s->dstat);
+        AVS_CUDA(avs_launch(finalize_kernel<1024>, dim3(nq), dim3(fin_threads), 0, st, pdl,
+                            s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.topkeys, c.topn, bound, eps_used, kprime, k,
+                            n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status,
+                            c.flagged, c.rep_thr, c.rep_cnt, s->dstat));
     s->st_launches++;
-    AVS_CUDA(cudaGetLastError());
-    wide_rescore_kernel<<<nq, 1024, AVS_WIDE_MAX * sizeof(Hit), st>>>(
-        s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, eps_used, k,
-        n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
-        c.rep_cnt, s->dstat);
+    AVS_CUDA(avs_launch(wide_rescore_kernel, dim3(nq), dim3(1024), AVS_WIDE_MAX * sizeof(Hit), st, pdl,
+                        s->master, s->ids, q, c.qnorm, s->dim, s->metric, c.cand, c.cnt, cap, c.tau, eps_used, k,
+                        n_eff, s->opt_force_repair, out_ids, out_scores, out_rows, c.out_s64, c.status, c.flagged, c.flagged2, c.rep_thr,
+                        c.rep_cnt, s->dstat));
     s->st_launches++;
-    AVS_CUDA(cudaGetLastError());
     {
         RepairArgs ra;
         ra.master = s->master; ra.q = q; ra.qnorm = c.qnorm; ra.ids = s->ids; ra.filt = s->filter;
         ra.n_rows = s->count; ra.n_eff = n_eff; ra.dim = s->dim; ra.metric = s->metric; ra.k = k; ra.group = rep_group;
+        ra.slice_max = AVS_REPAIR_CAP;
         ra.flagged2 = c.flagged2; ra.rep_thr = c.rep_thr; ra.rep_cnt = c.rep_cnt; ra.rep_sel = c.rep_sel;
         ra.pool_s = c.rep_s; ra.pool_row = c.rep_row; ra.pool_items = (int64_t)c.pool_items; ra.hist = c.rep_hist;
         ra.out_ids = out_ids; ra.out_scores = out_scores; ra.out_rows = out_rows; ra.out_s64 = c.out_s64; ra.status = c.status;
         ra.dstat = s->dstat; ra.gbar = c.gbar + 1; ra.err = reinterpret_cast<unsigned int*>(s->dstat + 3);
-        void* args[] = {&ra};
-        AVS_CUDA(cudaLaunchCooperativeKernel((const void*)repair_kernel, dim3((unsigned)(rep_ctas_per_sm[s->device & 63] * s->num_sms)),
-                                             dim3(REPAIR_THREADS), args, rep_smem, st));
+        // grid = what the device keeps resident (occupancy query above), like the persistent scan: its grid barriers
+        // cannot wait for a CTA that never starts.  With PDL the launch cannot carry the cooperative attribute.
+        const dim3 rep_grid((unsigned)(rep_ctas_per_sm[s->device & 63] * s->num_sms));
+        if (pdl) AVS_CUDA(avs_launch(repair_kernel, rep_grid, dim3(REPAIR_THREADS), rep_smem, st, true, ra));
+        else {
+            void* args[] = {&ra};
+            AVS_CUDA(cudaLaunchCooperativeKernel((const void*)repair_kernel, rep_grid, dim3(REPAIR_THREADS), args, rep_smem, st));
+        }
         s->st_launches++;
     }
     AVS_CUDA(cudaEventRecord(pev, st));
@@ -1486,7 +1628,7 @@ extern "C" int avs_search_host(avs_store* s, const float* q_host, int nq, int k,
                                float* out_scores_host, int64_t* out_rows_host) {
     if (!s) { avs_set_error("avs_search_host: NULL store"); return AVS_E_INVALID; }
     if (nq < 0 || (nq > 0 && (!q_host || !out_ids_host || !out_scores_host))) { avs_set_error("avs_search_host: NULL buffer"); return AVS_E_INVALID; }
-    if (k < 1 || k > AVS_MAX_KPRIME) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_KPRIME); return AVS_E_INVALID; }
+    if (k < 1 || k > AVS_MAX_LIMIT) { avs_set_error("avs_search: limit %d outside [1, %d]", k, AVS_MAX_LIMIT); return AVS_E_INVALID; }
     if (nq == 0) return AVS_OK;
     AVS_CUDA(cudaSetDevice(s->device));
     AVS_CHECK(avs_host_staging_reserve(s, nq, k));
@@ -1533,6 +1675,8 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "hybrid") s->opt_hybrid = value != 0;
     else if (k == "boot") s->opt_boot = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
+    else if (k == "pdl") s->opt_pdl = value != 0;
+    else if (k == "l2_prefetch") s->opt_l2_prefetch = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));
     else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);

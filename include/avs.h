@@ -92,7 +92,10 @@ int avs_load(const char* path, int device, avs_store** out);
  * normalises inside, /root/reference/milvus/RAG.py:264 sends norm~40 vectors);
  * out_ids [nq,k] int64 / out_scores [nq,k] fp32 device buffers owned by the caller.
  * out_rows (nullable) receives the local row index of every hit (metadata lookup key).
- * Asynchronous on `stream`. 1 <= k <= 256. */
+ * Asynchronous on `stream`. 1 <= k <= 16384 (MilvusClient's own ceiling).  Limits up to 256 run the fused
+ * bf16 scan + float64 rescoring pipeline; larger ones (the reference never asks for more than 5,
+ * /root/reference/milvus/search_embeddings.py:64) are served exactly, and more slowly, straight from the fp32
+ * master: three passes over it per 8 queries.  Sharded stores (avs_search_sharded*) take k <= 256. */
 int avs_search(avs_store* s, const float* q, int nq, int k,
                int64_t* out_ids, float* out_scores, int64_t* out_rows, void* stream);
 

@@ -91,6 +91,9 @@ def test_collection_management_and_errors(pkg, tmp_path):
     with pytest.raises(pkg.MilvusException):
         c.search("x", data=[[0.0] * 8], limit=0)
     with pytest.raises(pkg.MilvusException):
+        c.search("x", data=[[0.0] * 8], limit=16385)                      # MilvusClient's own ceiling is 16 384
+    assert c.search("x", data=[[0.0] * 8], limit=16384) == [[]]            # accepted (empty collection: no device work)
+    with pytest.raises(pkg.MilvusException):
         c.search("x", data=[[0.0] * 8], metric_type="L2")
     with pytest.raises(pkg.MilvusException):
         c.insert("x", [{"id": 1, "vector": [0.0] * 9}])

@@ -148,8 +148,11 @@ def test_edge_cases_empty_ragged_ties(pkg):
             st.search(np.ones((1, 15), np.float32), 4)
         with pytest.raises(pkg.AvsError):
             st.search(np.ones((1, 16), np.float32), 0)
+        got_ids, got_d = st.search(Q, 257)                                  # limits above 256: the exact master scan
+        exp_ids, exp_d, _ = fs.search(X, pk, Q, 257, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
         with pytest.raises(pkg.AvsError):
-            st.search(np.ones((1, 16), np.float32), 257)
+            st.search(np.ones((1, 16), np.float32), 16385)                  # MilvusClient's own ceiling is 16 384
     finally:
         st.close()
 
@@ -607,3 +610,102 @@ def test_snapshot_save_and_load_round_trip(pkg, tmp_path):
     assert c2.search("snap", data=Q[:4], limit=5, output_fields=["file_id"]) == before
     assert c2.get_collection_stats("snap")["row_count"] == 2000
     c.close(); c2.close()
+
+
+@pytest.mark.parametrize("metric", ["COSINE", "IP"])
+@pytest.mark.parametrize("n,d,nq,k", [(20_000, 128, 3, 300), (20_000, 128, 11, 1000), (3_000, 768, 2, 2048), (50_000, 64, 2, 5000),
+                                      (40_000, 32, 1, 16384), (700, 64, 2, 1000)])
+def test_limits_above_256_take_the_exact_master_scan(pkg, metric, n, d, nq, k):
+    """MilvusClient allows limit <= 16 384 (the reference never exceeds 5): limits above the fused pipeline's 256 are served by
+    the exact repair kernel straight from the fp32 master - histogram threshold search, collect, sort (in shared memory up
+    to a 4 096-row slice, in place in the pool beyond) - and must equal the oracle like any other search."""
+    X, ids, Q = _data(n, d, nq, seed=n + d + k)
+    st = pkg.Store(d, metric, capacity=n)
+    try:
+        st.insert(X, ids)
+        got_ids, got_d, got_rows = st.search(Q, k, return_rows=True)
+        exp_ids, exp_d, exp_rows = fs.search(X, ids, Q, k, metric)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert np.array_equal(got_rows, exp_rows)
+        assert st.stat("last_scan_path") == 3 and st.stat("uncertified_queries") == 0
+        # a small limit afterwards goes back to the fused pipeline on the same scratch
+        got_ids, got_d = st.search(Q, 7)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, 7, metric)
+        _check(got_ids, got_d, exp_ids, exp_d)
+        assert st.stat("last_scan_path") in (1, 2)
+    finally:
+        st.close()
+
+
+def test_large_limit_with_duplicate_rows_and_a_filter(pkg):
+    """Exact ties (identical rows, shuffled ids) inside a 1 000-hit list must fall to the smaller id; a row filter applies."""
+    rng = np.random.default_rng(5)
+    n, d, k = 12_000, 48, 1000
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[2000:2600] = X[1000]                                   # 600 identical rows in the tail of the list
+    ids = rng.permutation(n).astype(np.int64)
+    Q = (X[1000] + 0.3 * rng.standard_normal((2, d))).astype(np.float32)
+    st = pkg.Store(d, "COSINE", capacity=n)
+    try:
+        st.insert(X, ids)
+        got_ids, got_d = st.search(Q, k)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, k, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+        mask = rng.random(n) < 0.5
+        st.set_filter(mask)
+        got_ids, got_d = st.search(Q, k)
+        sub = np.nonzero(mask)[0]
+        exp_ids, exp_d, _ = fs.search(X[sub], ids[sub], Q, k, "COSINE")
+        _check(got_ids, got_d, exp_ids, exp_d)
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,metric", [(300_000, 128, 1, 10, "COSINE"), (200_000, 64, 200, 10, "IP"), (60_000, 256, 700, 100, "COSINE"),
+                                             (30_000, 64, 2, 10, "COSINE")])
+def test_programmatic_dependent_launch_changes_nothing(pkg, n, d, nq, k, metric):
+    """The kernels of a search are chained by programmatic dependent launch (option `pdl`, default on): every kernel
+    waits on the device for its predecessor before it reads anything.  Same hits as with plain stream-ordered launches
+    and as the oracle, over repeated searches (a stale read would show up as a difference between repeats)."""
+    X, ids, Q = _data(n, d, nq, seed=n + nq)
+    st = pkg.Store(d, metric, capacity=n)
+    try:
+        st.insert(X, ids)
+        exp_ids, exp_d, _ = fs.search(X, ids, Q, k, metric) if n * nq <= 3e7 else fs.search_large(X, ids, Q, k, metric)
+        for pdl in (1, 0, 1):
+            st.set_option("pdl", pdl)
+            for _ in range(3):
+                got_ids, got_d = st.search(Q, k)
+                _check(got_ids, got_d, exp_ids, exp_d)
+        st.set_option("pdl", 1)
+        st.set_option("force_repair", 2)                      # wide rescoring AND the exact repair kernel, PDL-launched
+        got_ids, got_d = st.search(Q[: min(nq, 40)], k)
+        _check(got_ids, got_d, exp_ids[: min(nq, 40)], exp_d[: min(nq, 40)])
+        assert st.stat("repaired_queries") >= min(nq, 40) and st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
+
+
+def test_rescoring_skips_only_candidates_that_cannot_reach_the_top_k(pkg):
+    """finalize rescoring drops candidates whose scan score is more than 2 eps under the k-th scan score.  Rows packed
+    closer together than eps (near-duplicates of the query at 1e-4 spacing) must all survive the cut and come back in
+    exact float64 order; widely spaced ones are cut without changing the result."""
+    rng = np.random.default_rng(11)
+    n, d, k = 80_000, 256, 10
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    base = rng.standard_normal(d).astype(np.float32)
+    for i in range(40):                                       # 40 rows within ~1e-4 of one another in cosine
+        X[5000 + 37 * i] = base + 1e-3 * (i + 1) * rng.standard_normal(d).astype(np.float32)
+    ids = rng.permutation(n).astype(np.int64)
+    Q = np.stack([base, base + 0.01 * rng.standard_normal(d).astype(np.float32), rng.standard_normal(d).astype(np.float32)])
+    for nq_rep in (1, 60):                                    # batch 3 (CTA select) and batch 180 (warp selects)
+        Qr = np.tile(Q, (nq_rep, 1))
+        st = pkg.Store(d, "COSINE", capacity=n)
+        try:
+            st.insert(X, ids)
+            got_ids, got_d = st.search(Qr, k)
+            exp_ids, exp_d, _ = fs.search(X, ids, Qr, k, "COSINE")
+            _check(got_ids, got_d, exp_ids, exp_d)
+            assert st.stat("uncertified_queries") == 0
+        finally:
+            st.close()
