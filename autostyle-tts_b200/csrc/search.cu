@@ -599,13 +599,17 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
     avs_pdl_trigger();
     avs_pdl_wait();                            // the scan (and, through it, prep) has completed
     const int q = blockIdx.x, t = threadIdx.x;
+    // independent loads first (the kernel is a chain of dependent DRAM round trips: every one taken off it counts)
+    const u64 key_raw = t < kprime ? topkeys[(size_t)q * kprime + t] : 0ull;
     const int n = topn[q];
+    const double eps_q = (double)eps[q];
+    const double qn = qnorm[q];
     const int need = (int64_t)k < n_rows ? k : (int)n_rows;
     // Which candidates can still reach the top-k?  With s_k the `need`-th best SCAN score of the list, `need` rows have
     // exact score >= s_k - eps, and a candidate whose scan score is below s_k - 2 eps has exact score < s_k - eps: it
     // cannot be among the `need` best and its 3 KB master row need not be fetched (C2: ~40 % of K' = 32).  The list
     // arrives unordered from the radix selects, so every key's rank is counted (K' <= 256 broadcast reads).
-    if (t < kprime) s_keys[t] = t < n ? topkeys[(size_t)q * kprime + t] : 0ull;
+    if (t < kprime) s_keys[t] = t < n ? key_raw : 0ull;
     if (t == 0) { s_cut = -INFINITY; s_nlive = 0; }
     __syncthreads();
     int my_rank = -1;
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
             int r = 0;
             for (int j = 0; j < kprime; ++j) r += s_keys[j] > my_key ? 1 : 0;
             my_rank = r;
-            if (r == need - 1) s_cut = (double)avs_key_score(my_key) - 2.0 * (double)eps[q];
+            if (r == need - 1) s_cut = (double)avs_key_score(my_key) - 2.0 * eps_q;
         }
     }
     __syncthreads();
@@ -630,10 +634,24 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
     while (P < n_live) P <<= 1;                // sorted size; P <= K'
     {   // K5: exact float64 rescoring, one warp per candidate (8 warps take the live candidates in turns)
         const int lane = t & 31, warp = t >> 5;
-        const double qn = qnorm[q];
         const float* qp = qraw + (size_t)q * dim;
         const int nwarps = (int)(blockDim.x >> 5);
         const bool vec = ((dim & 3) == 0) && ((reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(qp)) & 15) == 0;
+        // the scoring loops consume a row in slices (2 x 128-bit loads per lane in flight), i.e. several dependent DRAM
+        // round trips per row; asking the L2 for the whole rows first turns all but the first into L2 hits
+        const int row_lines = (dim * 4 + 127) >> 7;
+        if (THREADS <= 256 && vec && kprime >= 4 * nwarps) {
+            for (int c0 = warp * 4; c0 < n_live; c0 += 4 * nwarps)
+                for (int i = 0; i < 4 && c0 + i < n_live; ++i) {
+                    const char* rp = reinterpret_cast<const char*>(master + (size_t)s_live[c0 + i] * dim);
+                    for (int ln = lane; ln < row_lines; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ((size_t)ln << 7)));
+                }
+        } else {
+            for (int c = warp; c < n_live; c += nwarps) {
+                const char* rp = reinterpret_cast<const char*>(master + (size_t)s_live[c] * dim);
+                for (int ln = lane; ln < row_lines; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ((size_t)ln << 7)));
+            }
+        }
         if (THREADS <= 256 && vec && kprime >= 4 * nwarps) {
             // four candidates per warp at a time: their row loads overlap, the query is loaded once for the four
             for (int c0 = warp * 4; c0 < P; c0 += 4 * nwarps) {
@@ -648,12 +666,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
                     rows4[i] = s_live[c0 + i < n_live ? c0 + i : c0];   // the group's first row stands in for padding slots
                     xr[i] = master + (size_t)rows4[i] * dim;
                 }
+                const int64_t my_id = (lane < 4 && c0 + lane < n_live) ? ids[rows4[lane]] : INT64_MAX;   // in flight with the rows
                 double sc4[4];
                 exact_score_rows<4>(xr, qp, dim, qn, metric, lane, sc4);
                 if (lane < 4 && c0 + lane < P) {
                     Hit h;
                     const int c = c0 + lane;
-                    if (c < n_live) { h.row = rows4[lane]; h.s = sc4[lane]; h.id = ids[h.row]; }
+                    if (c < n_live) { h.row = rows4[lane]; h.s = sc4[lane]; h.id = my_id; }
                     else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
                     sm[c] = h;
                 }
@@ -663,14 +682,27 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
             Hit h;
             if (c < n_live) {
                 h.row = s_live[c];
+                h.id = ids[h.row];                                        // in flight with the row
                 h.s = exact_score(master + (size_t)h.row * dim, qp, dim, qn, metric, lane);
-                h.id = ids[h.row];
             } else { h.s = -INFINITY; h.id = INT64_MAX; h.row = 0xFFFFFFFFu; }
             if (lane == 0) sm[c] = h;
         }
         }
     }
     __syncthreads();
+    if (P <= 64) {
+        // short lists (K' = 32 for the reference's limits): every hit counts the hits that beat it - one pass of broadcast
+        // reads instead of the network's 15-21 barrier-separated stages; (score, id, row) is a strict total order
+        Hit mine;
+        int r = 0;
+        if (t < n_live) {                        // the padding entries behind the live ones stay where they are
+            mine = sm[t];
+            for (int j = 0; j < n_live; ++j) r += hit_better(sm[j], mine) ? 1 : 0;
+        }
+        __syncthreads();
+        if (t < n_live) sm[r] = mine;
+        __syncthreads();
+    } else
     for (int k2 = 2; k2 <= P; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
             if (t < P) {
@@ -694,7 +726,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) finalize_ker
     if (t == 0) {
         const float b = bound[q];
         bool ok = n >= need;
-        if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + (double)eps[q];
+        if (ok && need > 0 && b != -INFINITY) ok = sm[need - 1].s > (double)b + eps_q;
         if (force_repair) ok = false;
         if (!ok) {                                   // stage 1 of the repair: rescore the whole collected set
             const int pos = atomicAdd(flagged, 1);
