@@ -226,6 +226,7 @@ struct avs_store {
     int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
     int opt_l2_prefetch = 0;         // tensor-core scan, a single query block: L2 prefetch distance in k-blocks (0: off)
+    int opt_boot2_ratio = 0;         // compute-bound schedule: boot level directly in front of the final one up to this stride ratio (0: never)
     int opt_pdl = 1;                 // programmatic dependent launch between the kernels of a search
     int rank = 0, world = 1;
 };

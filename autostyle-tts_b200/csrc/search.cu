@@ -1416,7 +1416,20 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         // sparser boot level (up to cap / 32: 8 * ratio expected survivors fill a quarter of the buffer at most)
         int64_t rho_boot = rho;
         if (!fine_levels) { const int64_t m = cap / 32 < 128 ? cap / 32 : 128; rho_boot = rho > m ? rho : m; }
-        build_strides(boot_groups * AVS_GROUP_ROWS, 1, rho_boot);
+        // Small stores on the compute-bound schedule (a shard of a strongly scaled database): when the boot level can sit
+        // directly in front of the final level with a ratio of at most `boot2_ratio` and still deliver a rank <= J, the x4 level
+        // between them costs more (its tiles' epilogue, two grid barriers, a select) than the looser last threshold does.
+        bool two_level = false;
+        if (fine_levels && s->opt_boot2_ratio >= 2 && !s->eps_rule) {
+            int64_t r = (G + boot_groups - 1) / boot_groups;
+            if (r < 2) r = 2;
+            for (; r <= s->opt_boot2_ratio; ++r) {
+                strides[0] = 1; strides[1] = r; L = 2;
+                set_ranks();
+                if (j_ranks[0] <= AVS_BOOT_J) { two_level = true; break; }
+            }
+        }
+        if (!two_level) build_strides(boot_groups * AVS_GROUP_ROWS, 1, rho_boot);
         // the whole store inside the boot budget, but too large for ONE dense level: a boot level in front of the final one
         if (L == 1 && G * AVS_GROUP_ROWS > (cap < s->opt_gemm_dense_rows ? cap : s->opt_gemm_dense_rows)) {
             strides[1] = fine_levels ? s->opt_fine_ratio : 2;
@@ -1708,6 +1721,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "boot") s->opt_boot = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "pdl") s->opt_pdl = value != 0;
+    else if (k == "boot2_ratio") s->opt_boot2_ratio = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
     else if (k == "l2_prefetch") s->opt_l2_prefetch = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));

@@ -129,6 +129,11 @@ class Store:
         self.dim, self.metric, self.device = int(dim), metric, int(device)
         _check(self._lib, self._lib.avs_create(self.device, self.dim, METRIC_CODES[metric], int(capacity),
                                                ctypes.byref(self._h)))
+        # AVS_OPTS="key=value,...": engine options applied to every store (A/B runs of the whole test suite under a
+        # non-default schedule, profiles/); unset in normal use
+        for kv in filter(None, os.environ.get("AVS_OPTS", "").split(",")):
+            key, _, val = kv.partition("=")
+            self.set_option(key.strip(), int(val))
 
     # -- bulk snapshot ------------------------------------------------------------------------
     def save(self, path: str):
