@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--only-batch", action="store_true", help="skip the extra batch-1 measurement")
     ap.add_argument("--sweep", default="", help="comma-separated batch sizes measured on the same store; adds a `sweep` list to the JSON line")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllGather + merge instead of the fused peer-memory kernel")
-    ap.add_argument("--legs", default="auto", help="auto (C5 weak + C3 strong legs on the default workload), none, or a comma list of c5_weak,c3_strong")
+    ap.add_argument("--legs", default="auto", help="auto (C5 weak, C3 strong and C4 weak legs on the default workload), none, or a comma list of c5_weak,c3_strong,c4_weak")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s back-to-back loop")
     ap.add_argument("--leg-rows-scale", type=float, default=1.0, help="testing: scale the legs' row counts")
     return ap.parse_args()
@@ -652,7 +652,7 @@ def run_ours(a):
                 "steps": a.steps, "warmup": a.warmup, "full_oracle": a.rows * a.dim <= 1_100_000 * 1024,
                 "sustained": True, "cpu_baseline": True}
     default_workload = (a.rows, a.dim, a.k, a.metric) == (1_000_000, 768, 10, "COSINE")
-    want = [] if a.legs == "none" else (["c5_weak", "c3_strong"] if a.legs == "auto" else [x for x in a.legs.split(",") if x])
+    want = [] if a.legs == "none" else (["c5_weak", "c3_strong", "c4_weak"] if a.legs == "auto" else [x for x in a.legs.split(",") if x])
     if a.legs == "auto" and not default_workload:
         want = []
     sc = a.leg_rows_scale
@@ -662,6 +662,9 @@ def run_ours(a):
                     "batches": {1, 1024}, "main_batch": 1024, "steps": leg_steps, "warmup": leg_warm},
         "c3_strong": {"name": "c3_strong", "rows": int(10_000_000 * sc), "dim": 1024, "k": 10, "metric": "IP", "scaling": "strong",
                       "batches": {1, 4096}, "main_batch": 4096, "steps": leg_steps, "warmup": leg_warm},
+        # BASELINE.json configs[3]: 20 M x 3072 cosine top-50 over 8 GPUs = 2.5 M rows per GPU (weak scaling: N = 8 is the config itself)
+        "c4_weak": {"name": "c4_weak", "rows": int(2_500_000 * sc) * env.world, "dim": 3072, "k": 50, "metric": "COSINE", "scaling": "weak",
+                    "batches": {1, 1024}, "main_batch": 1024, "steps": leg_steps, "warmup": leg_warm},
     }
 
     m = measure(a, env, main_cfg)
