@@ -606,6 +606,102 @@ def measure(a, env, cfg):
             "cpu": cpu, "rows_local": rows_local, "exchange": exchange, "windows": headline_windows}
 
 
+def measure_c1(env):
+    """BASELINE.json configs[0] / SURVEY.md section 8(d) C1: the reference's own style database (tests/golden/f1_*: the
+    130 x 6144 rows of milvus/milvus_demo.db) through the reference's own call shape - `MilvusClient.search(collection,
+    data=[vec.tolist()], limit=5, output_fields=[...])`, one utterance at a time like milvus/search_json.py:382-449 and
+    the self-query loop of milvus/RAG.py:567-582.  Too small for a roofline: per-call latency (host wall clock around
+    the whole Python call, dict results included), parity against the golden top-5 lists, and the CPU port beside it."""
+    pkg = importlib.import_module("autostyle-tts_b200")
+    from oracle import flat_search as fs
+    G = os.path.join(ROOT, "tests", "golden")
+    X = np.load(os.path.join(G, "f1_vectors_fp16.npy")).astype(np.float32)
+    rows = json.load(open(os.path.join(G, "f1_rows.json"), encoding="utf-8"))
+    kat = np.load(os.path.join(G, "f1_kat.npz"))
+    pks, meta = rows["pks"], rows["meta"]
+    n, name = X.shape[0], "embeddings_biographies_collection"
+    client = pkg.MilvusClient(":memory:", device=env.local)
+    client.create_collection(collection_name=name, dimension=X.shape[1])
+    client.insert(collection_name=name, data=[{"id": int(pks[i]), "file_id": meta[i]["file_id"], "vector": X[i].tolist(),
+                                                "text": meta[i]["text"]} for i in range(n)])
+    row_of = {m["file_id"]: j for j, m in enumerate(meta)}
+    queries = [X[i].tolist() for i in range(n)]                       # the reference passes Python lists
+    for i in range(5):
+        client.search(collection_name=name, data=[queries[i]], limit=5, output_fields=["file_id", "text"])
+    lat, ok, max_rel = [], True, 0.0
+    for i in range(n):
+        t0 = time.perf_counter()
+        r = client.search(collection_name=name, data=[queries[i]], limit=5, output_fields=["file_id", "text"])
+        lat.append((time.perf_counter() - t0) * 1e3)
+        got_rows = [row_of[h["entity"]["file_id"]] for h in r[0]]
+        ok &= got_rows == kat["self_rows"][i].tolist() and [h["id"] for h in r[0]] == kat["self_pk_ids"][i].tolist()
+        max_rel = max(max_rel, float(np.max(np.abs(np.array([h["distance"] for h in r[0]], np.float32) - kat["self_dist"][i]))))
+    t0 = time.perf_counter()
+    rb = client.search(collection_name=name, data=X, limit=5, output_fields=["file_id", "text"])   # all 130 in one call
+    batch_ms = (time.perf_counter() - t0) * 1e3
+    ok &= all([row_of[h["entity"]["file_id"]] for h in rb[i]] == kat["self_rows"][i].tolist() for i in range(n))
+    rp = client.search(collection_name=name, data=kat["pert_queries"], limit=5, metric_type="COSINE", output_fields=["file_id"])
+    ok &= all([row_of[h["entity"]["file_id"]] for h in rp[i]] == kat["pert_rows"][i].tolist() for i in range(len(rp)))
+    client.close()
+    Xn = X / np.linalg.norm(X.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    cpu_lat = []
+    for i in range(n):                                                # the CPU port, one query per call as well
+        q = (X[i] / np.float32(np.linalg.norm(X[i].astype(np.float64))))[None, :]
+        t0 = time.perf_counter()
+        fs.cpu_flat_baseline(Xn, q, 5)
+        cpu_lat.append((time.perf_counter() - t0) * 1e3)
+    p10, p50, p90 = (float(x) for x in np.percentile(lat, [10, 50, 90]))
+    return {"config": {"workload": "C1: the reference's shipped style database (130 x 6144, tests/golden/f1_*), COSINE top-5, one query per call",
+                       "rows": n, "dim": int(X.shape[1]), "k": 5, "batch": 1},
+            "api": "MilvusClient.search(collection_name=, data=[list], limit=5, output_fields=[file_id, text]) - Python dicts out",
+            "latency_ms": {"p10": p10, "p50": p50, "p90": p90, "calls": n}, "qps": 1e3 / p50,
+            "one_call_all_130_queries_ms": batch_ms,
+            "cpu_port_latency_ms_p50": float(np.median(cpu_lat)), "cpu_port_qps": 1e3 / float(np.median(cpu_lat)),
+            "parity_ids_match_golden": bool(ok), "max_abs_distance_diff_vs_golden": max_rel,
+            "what": "top-5 rows, primary keys and distances of all 130 self-queries (KAT-2), the batched call and the 64 perturbed queries (C1) against tests/golden/f1_kat.npz"}
+
+
+def box_calibration(env):
+    """What THIS box's GPU delivers right now on the two library yardsticks the roofs in MEASURED_PEAKS.json were taken with:
+    a cuBLAS bf16 GEMM (8192^3, ~60 ms of back-to-back launches: a burst figure) and a device-to-device copy (1 GiB).
+    Context for `roofline.frac` only - the roofs stay the pool-wide measured peaks.  B200s of this pool differ by up to
+    ~35 % in tensor throughput under the 1 kW cap (profiles/r02: 1.12 vs 1.53 ms for the same batch-1024 search) while
+    their HBM-bound numbers agree to 1 %; nothing of the product runs here (cuBLAS via torch is the yardstick)."""
+    torch = env.torch
+    out = {}
+    try:
+        a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+        b = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+        for _ in range(5):
+            (a @ b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(80):
+            (a @ b)
+        e1.record()
+        torch.cuda.synchronize()
+        out["cublas_bf16_tflops"] = 80 * 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+        src = torch.empty(1 << 30, device="cuda", dtype=torch.uint8)
+        dst = torch.empty_like(src)
+        for _ in range(3):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            dst.copy_(src)
+        e1.record()
+        torch.cuda.synchronize()
+        out["copy_gbs"] = 20 * 2.0 * (1 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del src, dst
+        torch.cuda.empty_cache()
+        out["what"] = "torch bf16 matmul 8192^3 x 80 (cuBLAS) and 1 GiB device-to-device copy x 20 (read + write bytes), CUDA events, this GPU, before the searches"
+    except Exception as e:
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def leg_summary(cfg, m):
     out = {"config": {"rows_total": cfg["rows"], "rows_per_gpu": m["rows_local"], "dim": cfg["dim"], "k": cfg["k"],
                       "metric_type": cfg["metric"], "scaling": cfg["scaling"], "steps": cfg["steps"], "warmup": cfg["warmup"]},
@@ -645,6 +741,7 @@ def run_ours(a):
     env.windows = []
     if env.rank == 0:
         env.clocks.start()
+    calib = box_calibration(env) if env.rank == 0 else None
 
     sweep = sorted({int(b) for b in a.sweep.split(",") if b.strip()})
     main_cfg = {"name": "main", "rows": a.rows, "dim": a.dim, "k": a.k, "metric": a.metric, "scaling": "strong",
@@ -669,6 +766,14 @@ def run_ours(a):
 
     m = measure(a, env, main_cfg)
     legs = {}
+    if a.legs == "auto" and default_workload:
+        if env.world == 1:
+            try:
+                legs["c1_reference_db"] = measure_c1(env)
+            except Exception as e:
+                legs["c1_reference_db"] = {"error": f"{type(e).__name__}: {e}"}
+        else:
+            legs["c1_reference_db"] = None       # 130 rows do not shard: measured at N = 1 only
     for name in want:
         try:
             legs[name] = leg_summary(leg_cfgs[name], measure(a, env, leg_cfgs[name]))
@@ -696,7 +801,7 @@ def run_ours(a):
                            "scan_path": {1: "gemv", 2: "gemm"}.get(main["scan_path"]), "levels": main["levels"],
                            "oversample_kprime": main["kprime"], "gpu_launches_per_search": main["launches_per_search"],
                            "exchange_kernel_us": main["exchange_kernel_us"]},
-                "latency_ms": main["latency_ms"], "clocks": clk, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
+                "latency_ms": main["latency_ms"], "clocks": clk, "box_calibration": calib, "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
                 "cpu_baseline": cpu, "parity": m["parity"], "parity_ids_match_oracle": m["parity"].get("parity_ids_match_oracle"),
                 "planted_top1_match": m["planted_top1_match"], **m["stats"], "sustained": m["sustained"], "legs": legs}
         if 1 in results and a.batch != 1:
