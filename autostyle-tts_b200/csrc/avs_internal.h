@@ -121,7 +121,6 @@ struct AvsScanPlan {
     int n_levels;                       // levels scanned by this launch
     int last_is_final;                  // its last level is the final level of the search (select -> top K' + bound)
     int nq, kprime, cap;
-    int prefetch;                       // HBM-bound batches: L2 prefetch distance of the TMA producer in k-blocks (0: off)
     int64_t n_eff;                      // rows that may be returned (filter-allowed count)
     AvsLevel lv[AVS_MAX_LEVELS];
     int j_rank[AVS_MAX_LEVELS];
@@ -225,7 +224,6 @@ struct avs_store {
     int opt_finalize_threads = 0;    // 0: 1024 threads per query up to 64 queries, 256 beyond
     int opt_trace = 0;               // record per-level phase timestamps inside the persistent scan kernel
     int opt_fine_ratio = 4;          // stride ratio of the dense-end levels of the tensor-core path
-    int opt_l2_prefetch = 0;         // tensor-core scan, a single query block: L2 prefetch distance in k-blocks (0: off)
     int opt_boot2_ratio = 0;         // compute-bound schedule: boot level directly in front of the final one up to this stride ratio (0: never)
     int opt_pdl = 1;                 // programmatic dependent launch between the kernels of a search
     int rank = 0, world = 1;

@@ -82,20 +82,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// L2 prefetch of one box of a tensor map (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -349,51 +335,30 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (warp == 0) {
         // ===== TMA producer (one lane) =====
-        // One flat sequence of k-blocks over (level, tile, k-block).  HBM-bound batches (a single query block, option
-        // `l2_prefetch` = distance in k-blocks): whenever the ring is full the lane, instead of only spinning, asks the L2
-        // for database boxes further down ITS sequence (cp.async.bulk.prefetch.tensor), at most `prefetch` blocks ahead of
-        // the loads.  While the epilogue warps sit in a grid barrier or select a level, the MMA and the ring stand still
-        // (two accumulators of run-ahead) and so would the HBM stream; with the prefetch it keeps filling the L2.
+        // Tile coordinates are computed once per TILE (two 64-bit divisions), never per k-block: the lane has ~700 cycles
+        // per k-block on the compute-bound path, and a flat (level, tile, k-block) cursor that redid the divisions every
+        // k-block made this thread the bottleneck of the whole kernel (batch 1024: 1.13 -> 1.47 ms, profiles/r02/c26).
         if (lane == 0) {
             PipeState ps;
-            const int pf_max = n_qblocks == 1 ? plan.prefetch : 0;
-            auto level_tiles = [&](int l) { return plan.lv[l].n_visit * n_qblocks; };
-            // cursor over the sequence: (level, tile, k-block); `l == n_levels` = past the end
-            auto settle = [&](int& l, int64_t& t) { while (l < plan.n_levels && t >= level_tiles(l)) { ++l; t = cluster_id; } };
-            auto step = [&](int& l, int64_t& t, int& kb) {
-                if (++kb == num_k_blocks) { kb = 0; t += n_clusters; settle(l, t); }
-            };
-            int l = 0, kb = 0, pl = 0, pkb = 0;
-            int64_t t = cluster_id, pt = cluster_id;
-            settle(l, t);
-            pl = l; pt = t;
-            int64_t loaded = 0, prefetched = 0;
-            while (l < plan.n_levels) {
+            for (int l = 0; l < plan.n_levels; ++l) {
                 const AvsLevel& lv = plan.lv[l];
-                const int64_t m = t / n_qblocks;
-                const int qb = (int)(t - m * n_qblocks);
-                const int x_row = (int)(avs_level_group(lv, m) * BLOCK_N + cta_rank * C::LOAD_N);
-                const int q_row = (qb * CG + (int)cta_rank) * BLOCK_M;
-                const uint32_t eb = smem_u32(empty_bar + ps.stage);
-                if (pf_max > 0) {
-                    while (!mbar_try_wait(eb, ps.phase ^ 1)) {
-                        if (prefetched < loaded + pf_max && pl < plan.n_levels) {
-                            const int64_t pm = pt / n_qblocks;
-                            tma_prefetch_2d(&map_x, pkb * BLOCK_K, (int)(avs_level_group(plan.lv[pl], pm) * BLOCK_N + cta_rank * C::LOAD_N));
-                            step(pl, pt, pkb);
-                            ++prefetched;
-                        }
+                const int64_t n_tiles = lv.n_visit * n_qblocks;
+                for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                    const int64_t m = t / n_qblocks;
+                    const int qb = (int)(t - m * n_qblocks);
+                    const int64_t g = avs_level_group(lv, m);
+                    const int x_row = (int)(g * BLOCK_N + cta_rank * C::LOAD_N);
+                    const int q_row = (qb * CG + (int)cta_rank) * BLOCK_M;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        mbar_wait(smem_u32(empty_bar + ps.stage), ps.phase ^ 1);
+                        const uint32_t fb = smem_u32(full_bar + ps.stage);
+                        uint8_t* sa = smem + ps.stage * C::STAGE_BYTES;
+                        if (CG == 1 || leader) mbar_arrive_expect_tx(fb, C::STAGE_BYTES * CG);
+                        tma_load_2d<CG>(&map_q, fb, smem_u32(sa), kb * BLOCK_K, q_row, HINT_EVICT_LAST);
+                        tma_load_2d<CG>(&map_x, fb, smem_u32(sa + A_STAGE_BYTES), kb * BLOCK_K, x_row, HINT_EVICT_NORMAL);
+                        ps.template advance<C::STAGES>();
                     }
-                } else mbar_wait(eb, ps.phase ^ 1);
-                const uint32_t fb = smem_u32(full_bar + ps.stage);
-                uint8_t* sa = smem + ps.stage * C::STAGE_BYTES;
-                if (CG == 1 || leader) mbar_arrive_expect_tx(fb, C::STAGE_BYTES * CG);
-                tma_load_2d<CG>(&map_q, fb, smem_u32(sa), kb * BLOCK_K, q_row, HINT_EVICT_LAST);
-                tma_load_2d<CG>(&map_x, fb, smem_u32(sa + A_STAGE_BYTES), kb * BLOCK_K, x_row, HINT_EVICT_NORMAL);
-                ps.template advance<C::STAGES>();
-                step(l, t, kb);
-                ++loaded;
-                if (prefetched < loaded) { prefetched = loaded; pl = l; pt = t; pkb = kb; }   // the prefetch cursor never trails the loads
+                }
             }
         }
     } else if (warp == 1) {

@@ -1576,7 +1576,6 @@ int avs_search_local(avs_store* s, const float* q, int nq, int k, int64_t* out_i
         plan.n_levels = L - first_gemm_level;
         plan.last_is_final = 1;
         plan.nq = nq; plan.kprime = kprime; plan.cap = cap; plan.n_eff = n_eff;
-        plan.prefetch = s->opt_l2_prefetch;
         int64_t rows_scanned = 0;
         for (int l = first_gemm_level; l < L; ++l) {
             const int i = l - first_gemm_level;
@@ -1722,7 +1721,6 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "pdl") s->opt_pdl = value != 0;
     else if (k == "boot2_ratio") s->opt_boot2_ratio = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
-    else if (k == "l2_prefetch") s->opt_l2_prefetch = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));
     else if (k == "dense_rows") s->opt_dense_rows = value < 2048 ? 2048 : (value > AVS_DENSE_CAP ? AVS_DENSE_CAP : (int)value);

@@ -664,9 +664,10 @@ def measure_c1(env):
 def box_calibration(env):
     """What THIS box's GPU delivers right now on the two library yardsticks the roofs in MEASURED_PEAKS.json were taken with:
     a cuBLAS bf16 GEMM (8192^3, ~60 ms of back-to-back launches: a burst figure) and a device-to-device copy (1 GiB).
-    Context for `roofline.frac` only - the roofs stay the pool-wide measured peaks.  B200s of this pool differ by up to
-    ~35 % in tensor throughput under the 1 kW cap (profiles/r02: 1.12 vs 1.53 ms for the same batch-1024 search) while
-    their HBM-bound numbers agree to 1 %; nothing of the product runs here (cuBLAS via torch is the yardstick)."""
+    Context for `roofline.frac` only - the roofs stay the pool-wide measured peaks.  It separates "this box is slow" from
+    "this build is slow": a 30 % regression of the compute-bound path was first misread as box-to-box spread until the
+    same-box yardstick and an A/B against the previous library said otherwise (profiles/r02/c26).  Nothing of the product
+    runs here (cuBLAS via torch is the yardstick)."""
     torch = env.torch
     out = {}
     try:
