@@ -1720,6 +1720,7 @@ extern "C" int avs_set_option(avs_store* s, const char* key, int64_t value) {
     else if (k == "boot") s->opt_boot = value != 0;
     else if (k == "trace") s->opt_trace = value != 0;
     else if (k == "pdl") s->opt_pdl = value != 0;
+    else if (k == "eps_rule") s->eps_rule = value != 0;   // normally switched on by the first exact repair (tests force it)
     else if (k == "boot2_ratio") s->opt_boot2_ratio = value < 0 ? 0 : (value > 64 ? 64 : (int)value);
     else if (k == "finalize_threads") s->opt_finalize_threads = (value == 256 || value == 512 || value == 1024) ? (int)value : 0;
     else if (k == "gemm_dense_rows") s->opt_gemm_dense_rows = value < 256 ? 256 : (value > 2048 ? 2048 : (int)(value / 256 * 256));

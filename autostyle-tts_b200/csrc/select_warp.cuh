@@ -93,12 +93,17 @@ __device__ __forceinline__ void wsel_emit(const WarpSelectArgs& a, int q, int la
         return who ? __shfl_sync(0xffffffffu, v, __ffs(who) - 1) : 0ull;
     };
     if (!is_final) {
+        const u64 tau_old = a.tau[q];                                   // every lane reads it before lane 0 updates it below
+        __syncwarp();
         int keep = n_real >= jj ? jj : n_real;
-        u64 tau_new = n_real >= jj ? key_of_rank(jj - 1) : a.tau[q];
+        u64 tau_new = n_real >= jj ? key_of_rank(jj - 1) : tau_old;
         // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
         if (k_eps > 0 && n_real >= k_eps && !lost) {
             const u64 kk = key_of_rank(k_eps - 1);
-            const u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            // never below the threshold in force while these keys were collected: rows under THAT one were dropped
+            // already, and the final bound ("every row outside the buffer scores below tau") must hold for them too
+            if (t_eps < tau_old) t_eps = tau_old;
             if (t_eps < tau_new) {
                 tau_new = t_eps;
                 int above = 0;
@@ -268,9 +273,10 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
     for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
     const int n_real = nzc;
     const int want = is_final ? (n_real < a.kprime ? n_real : a.kprime) : (n_real >= jj ? jj : n_real);
-    u64 prefix = 0, maskb = 0;
-    int rank = want - 1;
-    if (want > 0) {
+    // the key of rank `rank0` (0-based, descending) among the real keys of c[0, n): 8 byte-wise histogram passes
+    auto radix_key = [&](int rank0) -> u64 {
+        u64 prefix = 0, maskb = 0;
+        int rank = rank0;
         for (int byte = 7; byte >= 0; --byte) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
@@ -309,15 +315,29 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
             rank -= sel_acc;
             __syncwarp();
         }
-    }
-    const u64 Pk = want > 0 ? prefix : ~0ull;                      // the rank-(want-1) key; exactly `want` keys are >= it
+        return prefix;
+    };
+    const u64 Pk = want > 0 ? radix_key(want - 1) : ~0ull;         // the rank-(want-1) key; exactly `want` keys are >= it
     if (!is_final) {
+        // Last threshold under the eps rule (see wsel_emit; round 2 found this path ignoring it: levels that collect more
+        // than 256 keys - half the queries of a 2.5 M x 3072 shard - kept the rank-j threshold, and ~1 % of them then
+        // failed the wide-rescoring certificate and paid for an exact scan of the fp32 master in EVERY search)
+        u64 thr = Pk;
+        bool lowered = false;
+        if (k_eps > 0 && n_real >= k_eps && !lost) {
+            const u64 kk = k_eps == want ? Pk : radix_key(k_eps - 1);
+            u64 t_eps = avs_make_key(avs_key_score(kk) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            const u64 tau_old = a.tau[q];                          // (lane 0 writes it only after the compaction's warp syncs)
+            if (t_eps < tau_old) t_eps = tau_old;                  // rows under the threshold in force were dropped already
+            const u64 tau_cur = n_real >= jj ? Pk : tau_old;
+            if (t_eps < tau_cur) { thr = t_eps; lowered = true; }
+        }
         // ordered in-place compaction: the write cursor never passes the read cursor
         int m = 0;
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
             const u64 key = i < n ? c[i] : 0ull;
-            const bool in = key >= Pk && key != 0ull;
+            const bool in = key >= thr && key != 0ull;
             const unsigned bal = __ballot_sync(0xffffffffu, in);
             __syncwarp();
             if (in) c[m + __popc(bal & ((1u << lane) - 1))] = key;
@@ -325,8 +345,8 @@ __device__ __noinline__ void warp_select_level(const WarpSelectArgs& a, int q, i
             __syncwarp();
         }
         if (lane == 0) {
-            if (n_real >= jj) a.tau[q] = Pk;
-            a.cnt[q] = want;
+            if (n_real >= jj || lowered) a.tau[q] = thr;
+            a.cnt[q] = m;                                          // == want unless the eps rule lowered the threshold
             if (lost) a.status[q] |= AVS_ST_OVERFLOW;
         }
     } else {
@@ -373,6 +393,7 @@ __device__ __noinline__ bool cta_select_fast(const WarpSelectArgs& a, int q, int
     u64* c = a.cand + (size_t)q * a.cap;
     const int total_in = dense_total > 0 ? dense_total : a.cnt[q];
     if (dense_total == 0 && total_in > a.cap) return false;          // keys were lost: the general path scales the rank
+    const u64 tau_old = a.tau[q];                                    // read by every thread BEFORE thread 0 may update it (below)
     const int n = total_in;
     // (under the eps rule the threshold may end up BELOW the pivot, whose compaction would already have dropped rows)
     const bool pivot_case = dense_total > 0 && !is_final && j_rank <= 32 && n > 512 && n <= 2048 && k_eps == 0;
@@ -449,11 +470,12 @@ __device__ __noinline__ bool cta_select_fast(const WarpSelectArgs& a, int q, int
     const int n_real = misc[1];
     if (!is_final) {
         int keep = n_real >= jj ? jj : n_real;
-        u64 tau_new = n_real >= jj ? pub[0] : a.tau[q];
+        u64 tau_new = n_real >= jj ? pub[0] : tau_old;
         bool lowered = false;
         // Last threshold (eps rule, see select_level_kernel): at least 2.5 eps below the k-th scan score seen so far
         if (k_eps > 0 && n_real >= k_eps) {
-            const u64 t_eps = avs_make_key(avs_key_score(pub[1]) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            u64 t_eps = avs_make_key(avs_key_score(pub[1]) - 2.5f * a.eps[q], 0xFFFFFFFFu);
+            if (t_eps < tau_old) t_eps = tau_old;                   // see wsel_emit: never below the threshold in force
             if (t_eps < tau_new) { tau_new = t_eps; lowered = true; }
         }
         if (lowered) {                                               // uniform: every thread read the same shared values

@@ -126,6 +126,33 @@ def test_c4_shard_d3072_k50_wide_and_repair_counters(pkg):
         st.close()
 
 
+def test_eps_rule_on_levels_that_collect_more_than_256_keys(pkg):
+    """Round 2, call 28: on a 2.5 M-row shard with k = 50 and batch 1024 the level in front of the final one collects
+    ~256 keys per query (rank 8 of the level before x a ratio of 32), so about half of the queries leave the register
+    select for the warp's radix select - which ignored the eps rule: those queries kept the plain rank-j threshold,
+    ~1 % of them then failed the wide-rescoring certificate and the exact fp32 scan (25 ms on 2.5 M x 3072) ran in EVERY
+    search.  Same schedule here at D = 128 (rows, k and batch decide the levels; the oracle stays affordable): with the
+    rule forced on, the answers equal the oracle's and nothing reaches the exact scan."""
+    synth = load_pkg("synth")
+    n, d, k, nq, n_check = 2_500_000, 128, 50, 1024, 256
+    st, X = _fill(pkg, n, d, "COSINE")
+    try:
+        Q = synth.planted_queries(43, 42, n, nq, d)
+        exp_ids, exp_d = _oracle_blocked(X, Q[:n_check], k, "COSINE")
+        ids, sc = st.search(Q, k)
+        assert st.stat("last_scan_path") == 2 and st.stat("last_levels") == 4
+        _compare(ids[:n_check], sc[:n_check], exp_ids, exp_d, "2.5 M x 128 batch 1024 (rank-j threshold)")
+        st.set_option("eps_rule", 1)
+        rep0 = st.stat("repaired_queries")
+        for rep in range(2):
+            ids, sc = st.search(Q, k)
+            _compare(ids[:n_check], sc[:n_check], exp_ids, exp_d, f"2.5 M x 128 batch 1024 (eps rule, search {rep})")
+        assert st.stat("repaired_queries") - rep0 <= 2, "with the eps rule the exact scan is the (very) rare path"
+        assert st.stat("uncertified_queries") == 0
+    finally:
+        st.close()
+
+
 def test_c5_shard_k100_batch_1024(pkg):
     """configs[4] at shard size: 2 M x 768, cosine top-100 (K' = 256, radix select), batch 1024 and batch 1."""
     synth = load_pkg("synth")
