@@ -143,8 +143,10 @@ int avs_p2p_connect(avs_store* s, const void* handles, int world);
  * "oversample" K' override (0=auto); "gemm_min_batch";
  * "levels_ratio"; "cta_group" 1|2 (tensor-core scan variant) and "cta_group_small" 1|2 (the variant for batches of at most
  * 128 queries; default 1: M = 128 queries per CTA, half the padded MMA work); schedule knobs "fine_ratio",
- * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "force_repair" (testing: 1 = force the
- * wide-rescoring stage, 2 = force the exact scan as well). */
+ * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "pdl" 0|1 (programmatic dependent launch between
+ * the kernels of a search, default 1); "trace" 0|1; "force_repair" (testing: 1 = force the wide-rescoring stage, 2 = force
+ * the exact scan as well); "eps_rule" 0|1 (testing: the last threshold is kept 2.5 eps under the k-th scan score - the
+ * engine switches this on by itself once a store has needed an exact repair). */
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),
