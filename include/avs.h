@@ -146,7 +146,10 @@ int avs_p2p_connect(avs_store* s, const void* handles, int world);
  * "fine_min_batch", "final_sigma", "coarse_sigma"; "p2p_merge" 0|1; "pdl" 0|1 (programmatic dependent launch between
  * the kernels of a search, default 1); "trace" 0|1; "force_repair" (testing: 1 = force the wide-rescoring stage, 2 = force
  * the exact scan as well); "eps_rule" 0|1 (testing: the last threshold is kept 2.5 eps under the k-th scan score - the
- * engine switches this on by itself once a store has needed an exact repair). */
+ * engine switches this on by itself once a store has needed an exact repair).  Measurement knobs kept for A/B runs:
+ * "boot2_ratio" (boot level directly in front of the final one up to this stride ratio; 0 = never, the default: measured
+ * negative), "finalize_threads" 0|256|512|1024, "gemm_dense_rows" / "dense_rows" (row caps of the threshold-free level of the
+ * tensor-core / warp-dot path when no boot level is built). */
 int avs_set_option(avs_store* s, const char* key, int64_t value);
 /* Counters since creation: "kernel_launches", "searches", "queries", "wide_rescored_queries" (certificate
  * reached after rescoring the whole collected set), "repaired_queries" (exact float64 scan needed),

@@ -289,3 +289,16 @@ def test_bench_reference_arm_runs_offline():
     line = json.loads(out.stdout.strip())
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "queries/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_every_option_and_stat_is_documented_in_the_header():
+    """include/avs.h is the contract a maintainer binds against: every key avs_set_option / avs_get_stat accepts must be
+    named in its comments (round 2 found four schedule knobs and the eps_rule / pdl switches missing)."""
+    import re
+    src = open(os.path.join(ROOT, "autostyle-tts_b200", "csrc", "search.cu"), encoding="utf-8").read()
+    hdr = open(os.path.join(ROOT, "include", "avs.h"), encoding="utf-8").read()
+    lo, mid = src.index('extern "C" int avs_set_option'), src.index('extern "C" int avs_get_stat')
+    keys = re.findall(r'k == "([a-z0-9_]+)"', src[lo:mid]) + re.findall(r'k == "([a-z0-9_]+)"', src[mid:])
+    assert len(keys) > 30
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, f"undocumented in include/avs.h: {missing}"
